@@ -1,0 +1,163 @@
+/*
+ * qvrcnn_b200.h -- C ABI of the B200-native QVRCNN int8 luma-enhancement pass.
+ *
+ * This is the drop-in boundary for ONE path of binbinmeng/QCNN_GPU: the static-BLU
+ * quantised VRCNN forward (`qvrcnn::forward_blu`) with its model / quant-param / YUV
+ * formats and its PSNR report.  The reference has no FFI of its own -- its operator
+ * surface is the C++ class `qvrcnn` (inference/qvrcnn.cuh:25-59) plus `vrcnn_data`
+ * (inference/yuv_data.h:11-27) -- so every entry point below names the reference
+ * member/function it replaces (paths relative to the reference repository).
+ * A header-only C++ shim with the reference's own class and method names sits on top
+ * of this ABI in qcnn_gpu_b200/csrc/qvrcnn.cuh and yuv_data.h.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success
+ * and a negative QV_ERR_* code on failure (the reference prints and exit(1)s --
+ * inference/cnn.cuh:8-15, inference/qvrcnn.cu:50-54 -- the C++ shim restores that);
+ * qv_last_error() returns a thread-local message for the last failure.
+ * A handle owns all of its device memory and streams, is bound to one CUDA device,
+ * and is not thread-safe; distinct handles may be used from distinct threads.
+ * There is no CPU fallback: without a CUDA device qv_create fails.
+ */
+#ifndef QVRCNN_B200_H
+#define QVRCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define QV_API __attribute__((visibility("default")))
+#else
+#define QV_API
+#endif
+
+typedef struct qv_net qv_net;
+
+enum {
+    QV_OK = 0,
+    QV_ERR_ARG = -1,      /* bad argument / null pointer / wrong size */
+    QV_ERR_IO = -2,       /* file cannot be opened / short read / bad format */
+    QV_ERR_CUDA = -3,     /* CUDA runtime failure (message in qv_last_error) */
+    QV_ERR_RANGE = -4,    /* model violates the exact-integer envelope (see qv_load_static_para) */
+    QV_ERR_STATE = -5     /* call order: e.g. forward before a model is loaded */
+};
+
+/* Kernel implementation selector (qv_set_impl). */
+enum {
+    QV_IMPL_AUTO = 0,     /* fused tcgen05 path when available, else per-layer */
+    QV_IMPL_LAYERED = 1,  /* per-layer CUDA-core dp4a kernels, activations in HBM */
+    QV_IMPL_FUSED = 2     /* whole net fused per strip, tcgen05.mma kind::i8 + TMEM */
+};
+
+/* Layer indices, order of the records in the model file (inference/qvrcnn.cu:55-60). */
+enum { QV_C1 = 0, QV_C2_1 = 1, QV_C2_2 = 2, QV_C3_1 = 3, QV_C3_2 = 4, QV_C4 = 5, QV_NLAYER = 6 };
+
+QV_API const char *qv_last_error(void);
+QV_API const char *qv_version(void);
+
+/* ---- network object: qvrcnn (inference/qvrcnn.cuh:25-59) -------------------------------- */
+
+/* qvrcnn::qvrcnn(gpu_num, batch, channel, height, width)   inference/qvrcnn.cu:4-29.
+   channel must be 1 (luma).  `batch` frames are held in the handle's own x / x_rec buffers. */
+QV_API int qv_create(int gpu_num, int batch, int channel, int height, int width, qv_net **out);
+/* qvrcnn::~qvrcnn   inference/qvrcnn.cu:331-335 */
+QV_API int qv_destroy(qv_net *net);
+
+/* qvrcnn::load_static_para(char*)   inference/qvrcnn.cu:47-63 -> CovLayer::load_static_para
+   inference/cnn.cu:90-112.  Reads the 60 028-byte NCHW_VECT_C static model file.
+   Returns QV_ERR_RANGE if some output channel has 128*sum|w| + |b| >= 2^24: beyond that the
+   reference's fp32 materialisation of u (inference/mat.cuh:69-70) stops being exact integer
+   arithmetic and this integer implementation would not be bit-identical. */
+QV_API int qv_load_static_para(qv_net *net, const char *filename);
+/* Same record stream from memory (for callers that hold the model image already). */
+QV_API int qv_load_static_para_mem(qv_net *net, const void *image, size_t len);
+/* HWCN-flavoured static model file (input of model_qfp_HWCN2NCHW_VECT_C,
+   inference/qvrcnn.cu:535-585), converted on load. */
+QV_API int qv_load_static_para_hwcn(qv_net *net, const char *filename);
+
+/* Per-QP scale file written by training/quantization.py:90-96 -- either the pickle
+   `quant_params<QP>.data` or the raw `quant_params_cpp_<QP>.data` (6 x 6 doubles).
+   Installs blu_q / mul / shift for the six layers (the only fields inference consumes,
+   inference/cnn.cu:101-103). */
+QV_API int qv_load_quant_params(qv_net *net, const char *filename);
+/* Parse only: out18 = {blu, mul, shift} x 6. */
+QV_API int qv_read_quant_params(const char *filename, int32_t *out18);
+/* Install weights of one layer as plain [K][C][R][S] int8 + int32 bias[K]
+   (what CovLayer::load_static_para leaves in w / b, inference/cnn.cu:99-106, minus the
+   NCHW_VECT_C packing). */
+QV_API int qv_set_weights(qv_net *net, int layer, const int8_t *w_kcrs, const int32_t *bias);
+/* Read back what inference will use: out18 = {blu, mul, shift} x 6. */
+QV_API int qv_get_quant_params(const qv_net *net, int32_t *out18);
+
+/* qvrcnn::load_data(datatype*)   inference/qvrcnn.cu:64-68 -> InputLayer::load cnn.cu:439-443.
+   Copies batch*height*width bytes of luma from host memory into the handle. */
+QV_API int qv_load_data(qv_net *net, const uint8_t *host_luma);
+/* qvrcnn::forward_blu()   inference/qvrcnn.cu:168-242.  Synchronous like the reference
+   (which synchronises after every layer); on return x_rec is complete. */
+QV_API int qv_forward_blu(qv_net *net);
+/* Replaces the driver's direct poke `cudaMemcpy(recon, qvrcnn1.I1.x_rec, ...)`
+   inference/kernel.cu:96: copies batch*height*width bytes of reconstructed luma to host. */
+QV_API int qv_get_recon(qv_net *net, uint8_t *host_out);
+
+/* The hot loop of testqvrcnn (inference/kernel.cu:91-97: per frame load_data, forward_blu,
+   sync, D2H) over n_frames host frames, pipelined: pinned staging, H2D / compute / D2H
+   overlapped on private streams, `batch` frames per chunk.  h_in / h_out may be pageable. */
+QV_API int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int n_frames);
+/* Same pass on frames already resident in device memory (n_frames may exceed `batch`);
+   asynchronous on `cuda_stream` (a cudaStream_t, NULL = the handle's own stream, in which
+   case the call synchronises before returning). */
+QV_API int qv_forward_frames_device(qv_net *net, const uint8_t *d_in, uint8_t *d_out, int n_frames,
+                                    void *cuda_stream);
+/* Spatially partitioned pass for one very large frame (multi-GPU strips): the frame has
+   img_height x width pixels (width = the handle's); d_in points at image row `in_row0` and holds
+   `in_rows` rows (the strip plus up to 6 halo rows each side); rows [out_row0, out_row1) are
+   written to d_out (whose first row is out_row0).  Activations outside the IMAGE are zero
+   (each layer's own SAME padding, inference/cnn.cu:44-49); rows outside the strip but inside
+   the image are recomputed from the halo. */
+QV_API int qv_forward_rows_device(qv_net *net, const uint8_t *d_in, int img_height, int in_row0, int in_rows,
+                                  uint8_t *d_out, int out_row0, int out_row1, void *cuda_stream);
+
+/* Explicit device-pointer accessor for drivers that, like the reference's, read the object's
+   buffers directly (`qvrcnn1.I1.x_rec`, inference/kernel.cu:96; InputLayer::x / x_rec,
+   inference/cnn.cuh:98).  The pointers stay owned by the handle. */
+QV_API int qv_device_buffers(qv_net *net, void **d_x, void **d_x_rec);
+
+/* Sum of squared errors between two device luma buffers of n bytes (exact int64), the integer
+   core of vrcnn_data::psnr (inference/yuv_data.cpp:87-97).  *d_sse_accum (device int64) is
+   incremented; asynchronous on cuda_stream. */
+QV_API int qv_sse_device(const uint8_t *d_a, const uint8_t *d_b, size_t n, int64_t *d_sse_accum, void *cuda_stream);
+
+/* Implementation / debug controls (no reference counterpart). */
+QV_API int qv_set_impl(qv_net *net, int impl);
+QV_API int qv_get_impl(const qv_net *net);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+QV_API long long qv_launch_count(const qv_net *net);
+/* Debug taps of the LAYERED path, valid after qv_forward_blu: copies frame 0's activations to
+   host as planar int8 [C][H][W] (a1: 64, a2: 48, a3: 48 channels) -- the contents of C1.v,
+   Conc1.conc, Conc2.conc in the reference (inference/qvrcnn.cu:183,202,218). */
+QV_API int qv_get_activation(qv_net *net, int which /*1,2,3*/, int8_t *host_out);
+
+/* ---- model-file converters ------------------------------------------------- */
+/* model_qfp_HWCN2NCHW_VECT_C   inference/qvrcnn.cu:558-585 */
+QV_API int qv_convert_model_hwcn_to_vect_c(const char *file_in, const char *file_out);
+
+/* ---- luma frame I/O + PSNR: vrcnn_data (inference/yuv_data.h:11-27) ---------------------- */
+/* vrcnn_data::read_data   inference/yuv_data.cpp:15-42: luma of the first `frames` frames of
+   a YUV 4:2:0 8-bit planar file. */
+QV_API int qv_yuv_read_luma(const char *filename, int frames, int height, int width, uint8_t *out);
+/* vrcnn_data::read_frame   inference/yuv_data.cpp:44-66: luma of frame n. */
+QV_API int qv_yuv_read_frame(const char *filename, int n, int height, int width, uint8_t *out);
+/* vrcnn_data::save_recon_as   inference/yuv_data.cpp:113-128: Y plane then h*w/2 zero bytes. */
+QV_API int qv_yuv_write_recon(const char *filename, const uint8_t *luma, int frames, int height, int width);
+/* vrcnn_data::psnr   inference/yuv_data.cpp:87-97 (pooled over n samples). */
+QV_API double qv_psnr(const uint8_t *data, const uint8_t *ori, size_t n, int64_t *sse_out);
+/* PSNR from an (all-reduced) integer SSE: mse = sse/n; 10*log10(65025/mse). */
+QV_API double qv_psnr_from_sse(int64_t sse, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QVRCNN_B200_H */

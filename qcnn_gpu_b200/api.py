@@ -1,0 +1,240 @@
+"""ctypes binding of the C ABI (include/qvrcnn_b200.h) with the reference's object names.
+
+`QVRCNN` mirrors class qvrcnn (inference/qvrcnn.cuh:25-59): same constructor arguments, same
+method names (`load_static_para`, `load_data`, `forward_blu`) and the same error behaviour
+translated to Python (the reference prints and exit(1)s; here a `QVError` is raised).
+`VRCNNData` mirrors class vrcnn_data (inference/yuv_data.h:11-27).
+
+There is NO CPU fallback and nothing here touches oracle/: if libqvrcnn_b200.so is missing the
+import of the library fails loudly, and without a CUDA device `QVRCNN(...)` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libqvrcnn_b200.so")
+
+IMPL_AUTO, IMPL_LAYERED, IMPL_FUSED = 0, 1, 2
+
+# Every symbol include/qvrcnn_b200.h declares (tests check the built library exports them all).
+ABI_SYMBOLS = (
+    "qv_last_error", "qv_version", "qv_create", "qv_destroy", "qv_load_static_para",
+    "qv_load_static_para_mem", "qv_load_static_para_hwcn", "qv_load_quant_params", "qv_read_quant_params",
+    "qv_set_weights", "qv_get_quant_params", "qv_load_data", "qv_forward_blu", "qv_get_recon",
+    "qv_forward_frames_host", "qv_forward_frames_device", "qv_forward_rows_device", "qv_device_buffers",
+    "qv_sse_device",
+    "qv_set_impl", "qv_get_impl", "qv_launch_count", "qv_get_activation",
+    "qv_convert_model_hwcn_to_vect_c", "qv_yuv_read_luma", "qv_yuv_read_frame", "qv_yuv_write_recon",
+    "qv_psnr", "qv_psnr_from_sse",
+)
+
+
+class QVError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("qvrcnn_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Loads libqvrcnn_b200.so (built by __graft_entry__.build() / `make -C qcnn_gpu_b200/csrc`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no fallback implementation)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i32, cp = C.c_void_p, C.c_int, C.c_char_p
+        L.qv_last_error.restype = cp
+        L.qv_version.restype = cp
+        L.qv_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
+        L.qv_destroy.argtypes = [vp]
+        L.qv_load_static_para.argtypes = [vp, cp]
+        L.qv_load_static_para_mem.argtypes = [vp, vp, C.c_size_t]
+        L.qv_load_static_para_hwcn.argtypes = [vp, cp]
+        L.qv_load_quant_params.argtypes = [vp, cp]
+        L.qv_read_quant_params.argtypes = [cp, vp]
+        L.qv_set_weights.argtypes = [vp, i32, vp, vp]
+        L.qv_get_quant_params.argtypes = [vp, vp]
+        L.qv_load_data.argtypes = [vp, vp]
+        L.qv_forward_blu.argtypes = [vp]
+        L.qv_get_recon.argtypes = [vp, vp]
+        L.qv_forward_frames_host.argtypes = [vp, vp, vp, i32]
+        L.qv_forward_frames_device.argtypes = [vp, vp, vp, i32, vp]
+        L.qv_forward_rows_device.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
+        L.qv_sse_device.argtypes = [vp, vp, C.c_size_t, vp, vp]
+        L.qv_set_impl.argtypes = [vp, i32]
+        L.qv_get_impl.argtypes = [vp]
+        L.qv_launch_count.argtypes = [vp]
+        L.qv_launch_count.restype = C.c_longlong
+        L.qv_get_activation.argtypes = [vp, i32, vp]
+        L.qv_convert_model_hwcn_to_vect_c.argtypes = [cp, cp]
+        L.qv_yuv_read_luma.argtypes = [cp, i32, i32, i32, vp]
+        L.qv_yuv_read_frame.argtypes = [cp, i32, i32, i32, vp]
+        L.qv_yuv_write_recon.argtypes = [cp, vp, i32, i32, i32]
+        L.qv_psnr.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_int64)]
+        L.qv_psnr.restype = C.c_double
+        L.qv_psnr_from_sse.argtypes = [C.c_int64, C.c_size_t]
+        L.qv_psnr_from_sse.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise QVError(rc, lib().qv_last_error().decode("utf-8", "replace"))
+
+
+def _b(path) -> bytes:
+    return os.fsencode(path)
+
+
+class QVRCNN:
+    """qvrcnn(gpu_num, batch, channel, height, width) -- inference/qvrcnn.cu:4-29."""
+
+    def __init__(self, gpu_num: int, batch: int, channel: int, height: int, width: int):
+        self._h = C.c_void_p()
+        self.batch, self.channel, self.height, self.width = batch, channel, height, width
+        _check(lib().qv_create(gpu_num, batch, channel, height, width, C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().qv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # -- model ---------------------------------------------------------------------------
+    def load_static_para(self, filename) -> int:                     # inference/qvrcnn.cu:47-63
+        _check(lib().qv_load_static_para(self._h, _b(filename)))
+        return 0
+
+    def load_static_para_mem(self, image: bytes) -> int:
+        _check(lib().qv_load_static_para_mem(self._h, image, len(image)))
+        return 0
+
+    def load_static_para_hwcn(self, filename) -> int:
+        _check(lib().qv_load_static_para_hwcn(self._h, _b(filename)))
+        return 0
+
+    def load_quant_params(self, filename) -> int:
+        _check(lib().qv_load_quant_params(self._h, _b(filename)))
+        return 0
+
+    def set_weights(self, layer: int, w_kcrs: np.ndarray, bias: np.ndarray) -> int:
+        w = np.ascontiguousarray(w_kcrs, np.int8)
+        b = np.ascontiguousarray(bias, np.int32)
+        _check(lib().qv_set_weights(self._h, layer, w.ctypes.data, b.ctypes.data))
+        return 0
+
+    def quant_params(self) -> np.ndarray:
+        q = np.zeros(18, np.int32)
+        _check(lib().qv_get_quant_params(self._h, q.ctypes.data))
+        return q.reshape(6, 3)
+
+    # -- the reference's per-frame surface ------------------------------------------------
+    def load_data(self, input_u8: np.ndarray) -> int:                # inference/qvrcnn.cu:64-68
+        x = np.ascontiguousarray(input_u8, np.uint8)
+        assert x.size == self.batch * self.height * self.width, x.shape
+        _check(lib().qv_load_data(self._h, x.ctypes.data))
+        return 0
+
+    def forward_blu(self) -> int:                                    # inference/qvrcnn.cu:168-242
+        _check(lib().qv_forward_blu(self._h))
+        return 0
+
+    def get_recon(self) -> np.ndarray:                               # kernel.cu:96 (I1.x_rec D2H)
+        out = np.empty((self.batch, self.height, self.width), np.uint8)
+        _check(lib().qv_get_recon(self._h, out.ctypes.data))
+        return out
+
+    # -- batched variants ------------------------------------------------------------------
+    def forward_frames_host(self, frames_u8: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        x = np.ascontiguousarray(frames_u8, np.uint8)
+        n = x.size // (self.height * self.width)
+        if out is None:
+            out = np.empty_like(x)
+        _check(lib().qv_forward_frames_host(self._h, x.ctypes.data, out.ctypes.data, n))
+        return out
+
+    def forward_frames_host_ptr(self, in_ptr: int, out_ptr: int, n: int) -> None:
+        _check(lib().qv_forward_frames_host(self._h, in_ptr, out_ptr, n))
+
+    def forward_frames_device(self, d_in: int, d_out: int, n: int, stream: int = 0) -> None:
+        _check(lib().qv_forward_frames_device(self._h, d_in, d_out, n, stream or None))
+
+    def forward_rows_device(self, d_in: int, img_height: int, in_row0: int, in_rows: int, d_out: int,
+                            out_row0: int, out_row1: int, stream: int = 0) -> None:
+        _check(lib().qv_forward_rows_device(self._h, d_in, img_height, in_row0, in_rows, d_out, out_row0,
+                                            out_row1, stream or None))
+
+    # -- controls ---------------------------------------------------------------------------
+    def set_impl(self, impl: int) -> None:
+        _check(lib().qv_set_impl(self._h, impl))
+
+    def get_impl(self) -> int:
+        return lib().qv_get_impl(self._h)
+
+    def launch_count(self) -> int:
+        return int(lib().qv_launch_count(self._h))
+
+    def get_activation(self, which: int) -> np.ndarray:
+        out = np.empty((64 if which == 1 else 48, self.height, self.width), np.int8)
+        _check(lib().qv_get_activation(self._h, which, out.ctypes.data))
+        return out
+
+
+def sse_device(d_a: int, d_b: int, n: int, d_accum: int, stream: int = 0) -> None:
+    _check(lib().qv_sse_device(d_a, d_b, n, d_accum, stream or None))
+
+
+def read_quant_params(filename) -> np.ndarray:
+    q = np.zeros(18, np.int32)
+    _check(lib().qv_read_quant_params(_b(filename), q.ctypes.data))
+    return q.reshape(6, 3)
+
+
+def convert_model_hwcn_to_vect_c(file_in, file_out) -> None:
+    _check(lib().qv_convert_model_hwcn_to_vect_c(_b(file_in), _b(file_out)))
+
+
+def psnr_from_sse(sse: int, n: int) -> float:
+    return float(lib().qv_psnr_from_sse(sse, n))
+
+
+class VRCNNData:
+    """vrcnn_data(frame, height, width) -- inference/yuv_data.cpp:3-14: host buffers ori / input /
+    recon of frame*h*w bytes each."""
+
+    def __init__(self, frame: int, height: int, width: int):
+        self.frame, self.h, self.w = frame, height, width
+        self.nSize = frame * height * width
+        self.ori = np.zeros((frame, height, width), np.uint8)
+        self.input = np.zeros((frame, height, width), np.uint8)
+        self.recon = np.zeros((frame, height, width), np.uint8)
+
+    def read_data(self, orifile, inputfile) -> int:                  # inference/yuv_data.cpp:15-42
+        _check(lib().qv_yuv_read_luma(_b(orifile), self.frame, self.h, self.w, self.ori.ctypes.data))
+        _check(lib().qv_yuv_read_luma(_b(inputfile), self.frame, self.h, self.w, self.input.ctypes.data))
+        return 0
+
+    def read_frame(self, orifile, inputfile, n: int) -> int:         # inference/yuv_data.cpp:44-66
+        self.frame = 1
+        _check(lib().qv_yuv_read_frame(_b(orifile), n, self.h, self.w, self.ori.ctypes.data))
+        _check(lib().qv_yuv_read_frame(_b(inputfile), n, self.h, self.w, self.input.ctypes.data))
+        return 0
+
+    def psnr(self, data: np.ndarray) -> float:                       # inference/yuv_data.cpp:87-97
+        d = np.ascontiguousarray(data, np.uint8)
+        return float(lib().qv_psnr(d.ctypes.data, self.ori.ctypes.data, self.nSize, None))
+
+    def save_recon_as(self, filename) -> int:                        # inference/yuv_data.cpp:113-128
+        _check(lib().qv_yuv_write_recon(_b(filename), self.recon.ctypes.data, self.frame, self.h, self.w))
+        return 0

@@ -1,0 +1,115 @@
+// qcnn_gpu -- the reference's driver (inference/kernel.cu:74-138: main -> run_all -> testqvrcnn)
+// rebuilt on the shim classes.  Same positional CLI:   qcnn_gpu <ori.yuv> <anchor_prefix> <H> <W>
+// with the anchor file named <prefix>Q<qp>.yuv (kernel.cu:124), the same report lines
+// ("before net:PSNR=", "after quantized net:PSNR=", "time:") appended to log.txt and the PSNR double
+// appended to recon_psnr.data (kernel.cu:107-115).  Additions, all optional trailing arguments:
+//   --model <printf-template with %d for QP>   (the reference hard-codes D:\...\qvrcnn_nchw_vect_c_8bit_qfp_%d.data)
+//   --qp <list>  e.g. 22,27,32,37 (reference loop: 22 only, kernel.cu:122)   --frames <n>
+//   --gpus <n>   frame-sharded over n devices, one host thread per device (no communication;
+//                the exact int64 SSE partial sums are added on the host)
+//   --save-recon <file>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "qvrcnn.cuh"
+
+struct Options {
+    std::string model_tmpl = "qvrcnn_nchw_vect_c_8bit_qfp_%d.data";
+    std::vector<int> qps{22};
+    int frames = 1, gpus = 1;
+    std::string save_recon;
+};
+
+static void testqvrcnn(const char *ori_fn, const char *input_fn, const char *model_fn, int frame, int channel, int height,
+                       int width, const Options &opt)
+{
+    vrcnn_data test_data(frame, height, width);
+    test_data.read_data(ori_fn, input_fn);
+    const size_t fpx = (size_t)channel * height * width;
+    const int G = opt.gpus;
+    std::vector<qvrcnn *> nets(G, nullptr);
+    for (int g = 0; g < G; ++g) {
+        int nf = frame / G + (g < frame % G ? 1 : 0);
+        nets[g] = new qvrcnn(g, nf > 0 ? std::min(nf, 8) : 1, channel, height, width);   // GPU_num,NCHW
+        nets[g]->load_static_para(model_fn);
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    if (G == 1 && frame == 1) {
+        // the reference's own per-frame sequence (kernel.cu:91-97)
+        nets[0]->load_data(test_data.input);
+        nets[0]->forward_blu();
+        cudaMemcpy(test_data.recon, (datatype *)nets[0]->I1.x_rec, fpx, cudaMemcpyDeviceToHost);
+    } else {
+        std::vector<std::thread> th;
+        int f0 = 0;
+        for (int g = 0; g < G; ++g) {
+            int nf = frame / G + (g < frame % G ? 1 : 0);
+            th.emplace_back([&, g, f0, nf] {
+                if (nf > 0) nets[g]->forward_frames(test_data.input + (size_t)f0 * fpx, test_data.recon + (size_t)f0 * fpx, nf);
+            });
+            f0 += nf;
+        }
+        for (auto &t : th) t.join();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    long long us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    for (auto *n : nets) delete n;
+    time_t now = time(0);
+    if (!opt.save_recon.empty()) test_data.save_recon_as(opt.save_recon.c_str());
+    double psnr1 = test_data.psnr(test_data.input);
+    double psnr2 = test_data.psnr(test_data.recon);
+    printf("\nbefore net:PSNR=%.3f\nafter quantized net:PSNR=%.3f\ntime:%lldus\n", psnr1, psnr2, us);
+    printf("throughput:%.1f Mpixel/s (%d frame(s) of %dx%d on %d GPU(s), host buffers, copies included)\n",
+           (double)frame * fpx / (double)us, frame, width, height, G);
+    FILE *logfile = fopen("log.txt", "a+");
+    if (!logfile) printf("write file failed\n");
+    else {
+        fprintf(logfile, "\nQVRCNN test date:%sdata:%s\nframes:%d\nheight:%d\nwidth:%d\nbefore net:PSNR=%f\nafter quantized net:PSNR=%f\ntime:%lldus\n",
+                ctime(&now), input_fn, frame, height, width, psnr1, psnr2, us);
+        fclose(logfile);
+    }
+    logfile = fopen("recon_psnr.data", "ab+");
+    if (!logfile) printf("open psnr file failed\n");
+    else { fwrite(&psnr2, sizeof(double), 1, logfile); fclose(logfile); }
+}
+
+static int run_all(const char *oriname, const char *inputname, int height, int width, const Options &opt)
+{
+    for (int qp : opt.qps) {
+        char input_fn[512], model_fn[512];
+        snprintf(input_fn, sizeof(input_fn), "%sQ%d.yuv", inputname, qp);           // kernel.cu:124
+        snprintf(model_fn, sizeof(model_fn), opt.model_tmpl.c_str(), qp);           // kernel.cu:125
+        testqvrcnn(oriname, input_fn, model_fn, opt.frames, 1, height, width, opt);
+    }
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 5) {
+        fprintf(stderr, "usage: %s <ori.yuv> <anchor_prefix> <H> <W> [--model tmpl%%d] [--qp 22,27,..] [--frames n] [--gpus n] [--save-recon f]\n", argv[0]);
+        return 2;
+    }
+    Options opt;
+    for (int i = 5; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--model" && i + 1 < argc) opt.model_tmpl = argv[++i];
+        else if (a == "--frames" && i + 1 < argc) opt.frames = atoi(argv[++i]);
+        else if (a == "--gpus" && i + 1 < argc) opt.gpus = atoi(argv[++i]);
+        else if (a == "--save-recon" && i + 1 < argc) opt.save_recon = argv[++i];
+        else if (a == "--qp" && i + 1 < argc) {
+            opt.qps.clear();
+            for (char *t = strtok(argv[++i], ","); t; t = strtok(nullptr, ",")) opt.qps.push_back(atoi(t));
+        } else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    if (opt.frames < 1 || opt.gpus < 1) { fprintf(stderr, "bad --frames/--gpus\n"); return 2; }
+    return run_all(argv[1], argv[2], atoi(argv[3]), atoi(argv[4]), opt);
+}

@@ -1,0 +1,489 @@
+// C ABI of the network object (include/qvrcnn_b200.h): handle lifetime, model loading,
+// the reference's load_data / forward_blu / x_rec read-back, and the batched / pipelined
+// variants the multi-GPU driver uses.  Mirrors class qvrcnn (inference/qvrcnn.cuh:25-59,
+// inference/qvrcnn.cu:4-68,168-242) and the hot loop of testqvrcnn (inference/kernel.cu:86-97).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "qv_fused.h"
+#include "qv_internal.h"
+#include "qv_layered.h"
+
+using namespace qv;
+
+#define QV_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return QV_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+struct qv_net {
+    int dev = 0, batch = 0, H = 0, W = 0;
+    cudaStream_t st = nullptr;
+    cudaStream_t pst[2] = {nullptr, nullptr};      // pipeline slots of qv_forward_frames_host
+    uint8_t *d_x = nullptr, *d_rec = nullptr;      // InputLayer::x / x_rec   (inference/cnn.cu:433-434)
+    uint8_t *d_slot_in[2] = {nullptr, nullptr}, *d_slot_out[2] = {nullptr, nullptr};
+    uint8_t *h_pin_in[2] = {nullptr, nullptr}, *h_pin_out[2] = {nullptr, nullptr};
+    int8_t *d_a1 = nullptr, *d_a2 = nullptr, *d_a3 = nullptr;   // C1.v / Conc1.conc / Conc2.conc (layered path)
+    int act_frames = 0;
+    uint8_t *d_rows_tmp = nullptr;
+    size_t rows_tmp_bytes = 0;
+    ModelHost model;
+    LayeredModel lm;
+    FusedModel *fm = nullptr;
+    bool uploaded = false;
+    int impl = QV_IMPL_AUTO;
+    long long launches = 0;
+};
+
+static int set_device(const qv_net *net) { QV_CUDA(cudaSetDevice(net->dev)); return QV_OK; }
+
+static void free_layered(qv_net *net)
+{
+    for (int l = 0; l < QV_NLAYER; ++l) {
+        cudaFree(net->lm.L[l].d_wpk);
+        cudaFree(net->lm.L[l].d_bias);
+        net->lm.L[l].d_wpk = nullptr;
+        net->lm.L[l].d_bias = nullptr;
+    }
+}
+
+static inline int pack4(const int8_t *p, int stride, int n)
+{
+    int v = 0;
+    for (int j = 0; j < n; ++j) v |= ((int)(uint8_t)p[j * stride]) << (8 * j);
+    return v;
+}
+
+// Re-pack the plain [K][C][R][S] host weights into the word layouts the layered kernels read.
+static int upload_layered(qv_net *net)
+{
+    free_layered(net);
+    for (int l = 0; l < QV_NLAYER; ++l) {
+        const LayerShape &s = kLayers[l];
+        const LayerHost &L = net->model.L[l];
+        std::vector<int32_t> wpk;
+        const int R = s.k;
+        if (l == QV_C1) {                        // [r][k][2]
+            wpk.assign(5 * 64 * 2, 0);
+            for (int r = 0; r < 5; ++r)
+                for (int k = 0; k < 64; ++k) {
+                    const int8_t *row = &L.w[((size_t)k * 5 + r) * 5];
+                    wpk[(r * 64 + k) * 2 + 0] = pack4(row, 1, 4);
+                    wpk[(r * 64 + k) * 2 + 1] = pack4(row + 4, 1, 1);
+                }
+        } else if (l == QV_C4) {                 // [tap][c4]
+            wpk.assign(9 * 12, 0);
+            for (int t = 0; t < 9; ++t)
+                for (int c4 = 0; c4 < 12; ++c4)
+                    wpk[t * 12 + c4] = pack4(&L.w[((size_t)(4 * c4) * 3 + t / 3) * 3 + t % 3], 9, 4);
+        } else {                                 // [group][tap][c4][16]
+            const int C4 = s.cin / 4, G = s.cout / 16;
+            wpk.assign((size_t)G * R * R * C4 * 16, 0);
+            for (int g = 0; g < G; ++g)
+                for (int t = 0; t < R * R; ++t)
+                    for (int c4 = 0; c4 < C4; ++c4)
+                        for (int j = 0; j < 16; ++j) {
+                            const int k = g * 16 + j;
+                            wpk[(((size_t)g * R * R + t) * C4 + c4) * 16 + j] =
+                                pack4(&L.w[(((size_t)k * s.cin + 4 * c4) * R + t / R) * R + t % R], R * R, 4);
+                        }
+        }
+        LayeredLayer &D = net->lm.L[l];
+        D.cout = s.cout;
+        D.q.blu = L.blu; D.q.mul = L.mul; D.q.shift = L.shift;
+        D.q.rbias = (1 << (L.shift - 1)) / L.mul;                       // inference/mat.cu:268
+        QV_CUDA(cudaMalloc(&D.d_wpk, wpk.size() * sizeof(int32_t)));
+        QV_CUDA(cudaMalloc(&D.d_bias, L.b.size() * sizeof(int32_t)));
+        QV_CUDA(cudaMemcpyAsync(D.d_wpk, wpk.data(), wpk.size() * sizeof(int32_t), cudaMemcpyHostToDevice, net->st));
+        QV_CUDA(cudaMemcpyAsync(D.d_bias, L.b.data(), L.b.size() * sizeof(int32_t), cudaMemcpyHostToDevice, net->st));
+        QV_CUDA(cudaStreamSynchronize(net->st));   // wpk is a local
+    }
+    net->lm.c4_bias = net->model.L[QV_C4].b[0];
+    return QV_OK;
+}
+
+static int validate_qparams(const ModelHost &m)
+{
+    for (int l = 0; l < QV_NLAYER; ++l) {
+        const LayerHost &L = m.L[l];
+        if (L.mul <= 0 || L.shift < 1 || L.shift > 30) {
+            set_error("layer %d: mul=%d shift=%d outside the supported range (mul>0, 1<=shift<=30)", l, L.mul, L.shift);
+            return QV_ERR_RANGE;
+        }
+        if (l != QV_C4 && (L.blu < 0 || L.blu >= (1 << 24))) {
+            set_error("layer %d: blu=%d outside [0, 2^24)", l, L.blu);
+            return QV_ERR_RANGE;
+        }
+    }
+    return QV_OK;
+}
+
+// Called whenever the host model changed; (re)builds device images once the model is complete.
+static int sync_model(qv_net *net)
+{
+    net->uploaded = false;
+    if (!net->model.complete()) return QV_OK;
+    int rc = validate_qparams(net->model);
+    if (rc) return rc;
+    rc = check_fp32_exact_envelope(net->model);
+    if (rc) return rc;
+    if ((rc = set_device(net))) return rc;
+    if ((rc = upload_layered(net))) return rc;
+    if (net->fm) { fused_free(net->fm); net->fm = nullptr; }
+    net->fm = fused_upload(net->model, net->st);     // may be null when the fused path is not built
+    net->uploaded = true;
+    return QV_OK;
+}
+
+static int ensure_acts(qv_net *net)
+{
+    if (net->d_a1) return QV_OK;
+    // C1.v, Conc1.conc, Conc2.conc of the reference (inference/cnn.cu:64,281), NHWC here; the
+    // reference also holds 644 B/px of fp32 `u` tensors which this design never materialises.
+    int frames = std::min(net->batch, 8);
+    const size_t px = (size_t)frames * net->H * net->W;
+    QV_CUDA(cudaMalloc(&net->d_a1, px * 64));
+    QV_CUDA(cudaMalloc(&net->d_a2, px * 48));
+    QV_CUDA(cudaMalloc(&net->d_a3, px * 48));
+    net->act_frames = frames;
+    return QV_OK;
+}
+
+static int run_forward(qv_net *net, const uint8_t *d_in, uint8_t *d_out, int n, int H, int W, cudaStream_t st)
+{
+    if (!net->uploaded) {
+        set_error("forward called before a complete model (weights + quant params) was loaded");
+        return QV_ERR_STATE;
+    }
+    int impl = net->impl;
+    if (impl == QV_IMPL_AUTO) impl = net->fm ? QV_IMPL_FUSED : QV_IMPL_LAYERED;
+    if (impl == QV_IMPL_FUSED) {
+        if (!net->fm) { set_error("fused tcgen05 path is not available in this build"); return QV_ERR_STATE; }
+        QV_CUDA(fused_forward(net->fm, d_in, d_out, n, H, W, st, &net->launches));
+        return QV_OK;
+    }
+    int rc = ensure_acts(net);
+    if (rc) return rc;
+    // activation scratch was sized for act_frames frames of net->H x net->W
+    const size_t cap_px = (size_t)net->act_frames * net->H * net->W;
+    const size_t fpx = (size_t)H * W;
+    if (fpx > cap_px) { set_error("frame of %dx%d exceeds the handle's activation scratch", W, H); return QV_ERR_ARG; }
+    const int chunk = (int)std::max<size_t>(1, cap_px / fpx);
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        const int c = std::min(chunk, n - f0);
+        QV_CUDA(layered_forward(net->lm, d_in + (size_t)f0 * fpx, d_out + (size_t)f0 * fpx, c, H, W, net->d_a1,
+                                net->d_a2, net->d_a3, st, &net->launches));
+    }
+    return QV_OK;
+}
+
+extern "C" {
+
+int qv_create(int gpu_num, int batch, int channel, int height, int width, qv_net **out)
+{
+    if (!out) { set_error("qv_create: null output pointer"); return QV_ERR_ARG; }
+    *out = nullptr;
+    if (channel != 1) { set_error("qv_create: channel must be 1 (luma), got %d", channel); return QV_ERR_ARG; }
+    if (batch < 1 || height < 1 || width < 1) { set_error("qv_create: bad geometry %dx%dx%d", batch, height, width); return QV_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("qv_create: no CUDA device (this library has no CPU fallback)");
+        return QV_ERR_CUDA;
+    }
+    if (gpu_num < 0 || gpu_num >= ndev) { set_error("qv_create: gpu_num %d out of range (%d devices)", gpu_num, ndev); return QV_ERR_ARG; }
+    QV_CUDA(cudaSetDevice(gpu_num));                                    // inference/qvrcnn.cu:6
+    qv_net *net = new qv_net();
+    net->dev = gpu_num; net->batch = batch; net->H = height; net->W = width;
+    const size_t bytes = (size_t)batch * height * width;
+    cudaError_t e = cudaStreamCreateWithFlags(&net->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&net->d_x, bytes);             // inference/cnn.cu:433
+    if (e == cudaSuccess) e = cudaMalloc(&net->d_rec, bytes);           // inference/cnn.cu:434
+    if (e != cudaSuccess) {
+        set_error("qv_create: %s", cudaGetErrorString(e));
+        qv_destroy(net);
+        return QV_ERR_CUDA;
+    }
+    *out = net;
+    return QV_OK;
+}
+
+int qv_destroy(qv_net *net)
+{
+    if (!net) return QV_OK;
+    cudaSetDevice(net->dev);
+    if (net->st) cudaStreamSynchronize(net->st);
+    free_layered(net);
+    if (net->fm) fused_free(net->fm);
+    cudaFree(net->d_x); cudaFree(net->d_rec);
+    cudaFree(net->d_a1); cudaFree(net->d_a2); cudaFree(net->d_a3);
+    cudaFree(net->d_rows_tmp);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(net->d_slot_in[i]); cudaFree(net->d_slot_out[i]);
+        cudaFreeHost(net->h_pin_in[i]); cudaFreeHost(net->h_pin_out[i]);
+        if (net->pst[i]) cudaStreamDestroy(net->pst[i]);
+    }
+    if (net->st) cudaStreamDestroy(net->st);
+    delete net;
+    return QV_OK;
+}
+
+int qv_load_static_para_mem(qv_net *net, const void *image, size_t len)
+{
+    if (!net || !image) { set_error("qv_load_static_para_mem: null argument"); return QV_ERR_ARG; }
+    ModelHost m;
+    int rc = parse_model_vect_c((const uint8_t *)image, len, m);
+    if (rc) return rc;
+    net->model = m;
+    return sync_model(net);
+}
+
+int qv_load_static_para(qv_net *net, const char *filename)
+{
+    if (!net) { set_error("qv_load_static_para: null handle"); return QV_ERR_ARG; }
+    std::vector<uint8_t> buf;
+    int rc = read_file(filename, buf);
+    if (rc) { set_error("cannot open model file. (%s)", filename ? filename : "(null)"); return rc; }   // qvrcnn.cu:52
+    return qv_load_static_para_mem(net, buf.data(), buf.size());
+}
+
+int qv_load_static_para_hwcn(qv_net *net, const char *filename)
+{
+    if (!net) { set_error("qv_load_static_para_hwcn: null handle"); return QV_ERR_ARG; }
+    std::vector<uint8_t> buf;
+    int rc = read_file(filename, buf);
+    if (rc) return rc;
+    ModelHost m;
+    rc = parse_model_hwcn(buf.data(), buf.size(), m);
+    if (rc) return rc;
+    net->model = m;
+    return sync_model(net);
+}
+
+int qv_load_quant_params(qv_net *net, const char *filename)
+{
+    if (!net) { set_error("qv_load_quant_params: null handle"); return QV_ERR_ARG; }
+    int32_t q[18];
+    int rc = qv_read_quant_params(filename, q);
+    if (rc) return rc;
+    for (int l = 0; l < QV_NLAYER; ++l) {
+        LayerHost &L = net->model.L[l];
+        L.blu = q[3 * l]; L.mul = q[3 * l + 1]; L.shift = q[3 * l + 2];
+        L.have_q = true;
+    }
+    return sync_model(net);
+}
+
+int qv_set_weights(qv_net *net, int layer, const int8_t *w_kcrs, const int32_t *bias)
+{
+    if (!net || !w_kcrs || !bias || layer < 0 || layer >= QV_NLAYER) { set_error("qv_set_weights: bad argument"); return QV_ERR_ARG; }
+    const LayerShape &s = kLayers[layer];
+    LayerHost &L = net->model.L[layer];
+    L.w.assign(w_kcrs, w_kcrs + (size_t)s.cout * s.cin * s.k * s.k);
+    L.b.assign(bias, bias + s.cout);
+    L.have_w = true;
+    return sync_model(net);
+}
+
+int qv_get_quant_params(const qv_net *net, int32_t *out18)
+{
+    if (!net || !out18) { set_error("qv_get_quant_params: null argument"); return QV_ERR_ARG; }
+    for (int l = 0; l < QV_NLAYER; ++l) {
+        out18[3 * l] = net->model.L[l].blu; out18[3 * l + 1] = net->model.L[l].mul; out18[3 * l + 2] = net->model.L[l].shift;
+    }
+    return QV_OK;
+}
+
+int qv_load_data(qv_net *net, const uint8_t *host_luma)
+{
+    if (!net || !host_luma) { set_error("qv_load_data: null argument"); return QV_ERR_ARG; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    const size_t bytes = (size_t)net->batch * net->H * net->W;
+    QV_CUDA(cudaMemcpyAsync(net->d_x, host_luma, bytes, cudaMemcpyHostToDevice, net->st));   // cnn.cu:441
+    QV_CUDA(cudaStreamSynchronize(net->st));
+    return QV_OK;
+}
+
+int qv_forward_blu(qv_net *net)
+{
+    if (!net) { set_error("qv_forward_blu: null handle"); return QV_ERR_ARG; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    rc = run_forward(net, net->d_x, net->d_rec, net->batch, net->H, net->W, net->st);
+    if (rc) return rc;
+    QV_CUDA(cudaStreamSynchronize(net->st));        // the reference is synchronous (kernel.cu:95)
+    return QV_OK;
+}
+
+int qv_get_recon(qv_net *net, uint8_t *host_out)
+{
+    if (!net || !host_out) { set_error("qv_get_recon: null argument"); return QV_ERR_ARG; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    const size_t bytes = (size_t)net->batch * net->H * net->W;
+    QV_CUDA(cudaMemcpyAsync(host_out, net->d_rec, bytes, cudaMemcpyDeviceToHost, net->st));   // kernel.cu:96
+    QV_CUDA(cudaStreamSynchronize(net->st));
+    return QV_OK;
+}
+
+int qv_forward_frames_device(qv_net *net, const uint8_t *d_in, uint8_t *d_out, int n_frames, void *cuda_stream)
+{
+    if (!net || !d_in || !d_out || n_frames < 0) { set_error("qv_forward_frames_device: bad argument"); return QV_ERR_ARG; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : net->st;
+    if (n_frames > 0) {
+        rc = run_forward(net, d_in, d_out, n_frames, net->H, net->W, st);
+        if (rc) return rc;
+    }
+    if (!cuda_stream) QV_CUDA(cudaStreamSynchronize(st));
+    return QV_OK;
+}
+
+int qv_forward_rows_device(qv_net *net, const uint8_t *d_in, int img_height, int in_row0, int in_rows, uint8_t *d_out,
+                           int out_row0, int out_row1, void *cuda_stream)
+{
+    if (!net || !d_in || !d_out) { set_error("qv_forward_rows_device: null argument"); return QV_ERR_ARG; }
+    // The net's receptive-field radius is 2+2+1+1 = 6 rows: treating the [in_row0, in_row0+in_rows)
+    // window as an image of its own is exact for every output row that is >= 6 rows away from a
+    // window edge, or whose window edge IS the image edge (where zero padding is the truth).
+    const int in_row1 = in_row0 + in_rows;
+    if (img_height < 1 || in_row0 < 0 || in_rows < 1 || in_row1 > img_height || out_row0 < in_row0 || out_row1 > in_row1 ||
+        out_row0 > out_row1) { set_error("qv_forward_rows_device: inconsistent row ranges"); return QV_ERR_ARG; }
+    if ((in_row0 != 0 && out_row0 - in_row0 < 6) || (in_row1 != img_height && in_row1 - out_row1 < 6)) {
+        set_error("qv_forward_rows_device: need 6 halo rows on every interior strip edge");
+        return QV_ERR_ARG;
+    }
+    int rc = set_device(net);
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : net->st;
+    const size_t W = net->W, need = (size_t)in_rows * W;
+    if ((size_t)in_rows * W > (size_t)net->batch * net->H * net->W && net->impl == QV_IMPL_LAYERED) {
+        set_error("qv_forward_rows_device: window larger than the handle's geometry");
+        return QV_ERR_ARG;
+    }
+    if (net->rows_tmp_bytes < need) {
+        QV_CUDA(cudaStreamSynchronize(st));
+        cudaFree(net->d_rows_tmp);
+        net->d_rows_tmp = nullptr; net->rows_tmp_bytes = 0;
+        QV_CUDA(cudaMalloc(&net->d_rows_tmp, need));
+        net->rows_tmp_bytes = need;
+    }
+    rc = run_forward(net, d_in, net->d_rows_tmp, 1, in_rows, net->W, st);
+    if (rc) return rc;
+    QV_CUDA(cudaMemcpyAsync(d_out, net->d_rows_tmp + (size_t)(out_row0 - in_row0) * W, (size_t)(out_row1 - out_row0) * W,
+                            cudaMemcpyDeviceToDevice, st));
+    if (!cuda_stream) QV_CUDA(cudaStreamSynchronize(st));
+    return QV_OK;
+}
+
+int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int n_frames)
+{
+    if (!net || !h_in || !h_out || n_frames < 0) { set_error("qv_forward_frames_host: bad argument"); return QV_ERR_ARG; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    const size_t fpx = (size_t)net->H * net->W;
+    const int chunk = net->batch;
+    const size_t cbytes = (size_t)chunk * fpx;
+    // Is the caller's memory page-locked already?  Then DMA straight from/to it.
+    cudaPointerAttributes ai{}, ao{};
+    bool pinned_in = cudaPointerGetAttributes(&ai, h_in) == cudaSuccess && ai.type == cudaMemoryTypeHost;
+    bool pinned_out = cudaPointerGetAttributes(&ao, h_out) == cudaSuccess && ao.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    for (int i = 0; i < 2; ++i) {
+        if (!net->pst[i]) QV_CUDA(cudaStreamCreateWithFlags(&net->pst[i], cudaStreamNonBlocking));
+        if (!net->d_slot_in[i]) QV_CUDA(cudaMalloc(&net->d_slot_in[i], cbytes));
+        if (!net->d_slot_out[i]) QV_CUDA(cudaMalloc(&net->d_slot_out[i], cbytes));
+        if (!pinned_in && !net->h_pin_in[i]) QV_CUDA(cudaMallocHost(&net->h_pin_in[i], cbytes));
+        if (!pinned_out && !net->h_pin_out[i]) QV_CUDA(cudaMallocHost(&net->h_pin_out[i], cbytes));
+    }
+    // Two slots, each an in-order H2D -> forward -> D2H chain on its own stream, so the copies of
+    // one chunk overlap the compute of the other (the reference's loop, inference/kernel.cu:91-97,
+    // is fully serial: blocking memcpy, forward, sync, blocking memcpy).
+    struct Pending { int f0 = -1, c = 0; } pend[2];
+    auto drain = [&](int s) -> int {
+        if (pend[s].f0 < 0) return QV_OK;
+        QV_CUDA(cudaStreamSynchronize(net->pst[s]));
+        if (!pinned_out) memcpy(h_out + (size_t)pend[s].f0 * fpx, net->h_pin_out[s], (size_t)pend[s].c * fpx);
+        pend[s].f0 = -1;
+        return QV_OK;
+    };
+    int slot = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, slot ^= 1) {
+        const int c = std::min(chunk, n_frames - f0);
+        const size_t bytes = (size_t)c * fpx;
+        if ((rc = drain(slot))) return rc;
+        const uint8_t *src = h_in + (size_t)f0 * fpx;
+        if (!pinned_in) { memcpy(net->h_pin_in[slot], src, bytes); src = net->h_pin_in[slot]; }
+        QV_CUDA(cudaMemcpyAsync(net->d_slot_in[slot], src, bytes, cudaMemcpyHostToDevice, net->pst[slot]));
+        rc = run_forward(net, net->d_slot_in[slot], net->d_slot_out[slot], c, net->H, net->W, net->pst[slot]);
+        if (rc) return rc;
+        uint8_t *dst = pinned_out ? h_out + (size_t)f0 * fpx : net->h_pin_out[slot];
+        QV_CUDA(cudaMemcpyAsync(dst, net->d_slot_out[slot], bytes, cudaMemcpyDeviceToHost, net->pst[slot]));
+        pend[slot].f0 = f0; pend[slot].c = c;
+    }
+    if ((rc = drain(0))) return rc;
+    if ((rc = drain(1))) return rc;
+    return QV_OK;
+}
+
+int qv_device_buffers(qv_net *net, void **d_x, void **d_x_rec)
+{
+    if (!net) { set_error("qv_device_buffers: null handle"); return QV_ERR_ARG; }
+    if (d_x) *d_x = net->d_x;
+    if (d_x_rec) *d_x_rec = net->d_rec;
+    return QV_OK;
+}
+
+int qv_sse_device(const uint8_t *d_a, const uint8_t *d_b, size_t n, int64_t *d_sse_accum, void *cuda_stream)
+{
+    if (!d_a || !d_b || !d_sse_accum) { set_error("qv_sse_device: null argument"); return QV_ERR_ARG; }
+    if (n == 0) return QV_OK;
+    QV_CUDA(sse_accumulate(d_a, d_b, n, d_sse_accum, (cudaStream_t)cuda_stream));
+    return QV_OK;
+}
+
+int qv_set_impl(qv_net *net, int impl)
+{
+    if (!net || impl < QV_IMPL_AUTO || impl > QV_IMPL_FUSED) { set_error("qv_set_impl: bad argument"); return QV_ERR_ARG; }
+    net->impl = impl;
+    return QV_OK;
+}
+
+int qv_get_impl(const qv_net *net)
+{
+    if (!net) return QV_ERR_ARG;
+    if (net->impl != QV_IMPL_AUTO) return net->impl;
+    return net->fm ? QV_IMPL_FUSED : QV_IMPL_LAYERED;
+}
+
+long long qv_launch_count(const qv_net *net) { return net ? net->launches : 0; }
+
+int qv_get_activation(qv_net *net, int which, int8_t *host_out)
+{
+    if (!net || !host_out || which < 1 || which > 3) { set_error("qv_get_activation: bad argument"); return QV_ERR_ARG; }
+    if (!net->d_a1) { set_error("qv_get_activation: the layered path has not run on this handle"); return QV_ERR_STATE; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    const int C = which == 1 ? 64 : 48;
+    const int8_t *src = which == 1 ? net->d_a1 : (which == 2 ? net->d_a2 : net->d_a3);
+    const size_t HW = (size_t)net->H * net->W;
+    int8_t *tmp = nullptr;
+    QV_CUDA(cudaMalloc(&tmp, HW * C));
+    cudaError_t e = nhwc_to_planar(src, tmp, C, HW, net->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, tmp, HW * C, cudaMemcpyDeviceToHost, net->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(net->st);
+    cudaFree(tmp);
+    QV_CUDA(e);
+    return QV_OK;
+}
+
+}  // extern "C"

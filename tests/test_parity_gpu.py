@@ -1,0 +1,237 @@
+"""Parity tests proper: the CUDA path through the C ABI vs the CPU oracle, bit for bit.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from qcnn_gpu_b200 import api
+from qcnn_gpu_b200.host import formats, synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+IMPLS = [api.IMPL_LAYERED, api.IMPL_FUSED]
+IMPL_NAME = {api.IMPL_LAYERED: "layered", api.IMPL_FUSED: "fused"}
+
+
+def _oracle(model):
+    from oracle import oracle
+    return oracle.OracleModel(formats.write_model_vect_c(model))
+
+
+def _net(model, batch, h, w, impl, tmp_path=None):
+    net = api.QVRCNN(0, batch, 1, h, w)
+    net.load_static_para_mem(formats.write_model_vect_c(model))
+    net.set_impl(impl)
+    return net
+
+
+def _fused_or_skip(net, impl):
+    if impl == api.IMPL_FUSED:
+        try:
+            net.set_impl(api.IMPL_FUSED)
+            x = np.zeros((net.batch, net.height, net.width), np.uint8)
+            net.load_data(x)
+            net.forward_blu()
+        except api.QVError as e:
+            if "not available" in str(e):
+                pytest.skip("fused path not built")
+            raise
+
+
+@pytest.mark.parametrize("impl", IMPLS, ids=lambda i: IMPL_NAME[i])
+@pytest.mark.parametrize("qp", [22, 27, 32, 37])
+def test_config1_416x240_bit_exact(models, qp, impl, tmp_path):
+    """BASELINE config 1 geometry (one 416x240 frame) for all four QP parameter sets, through the
+    reference's own call sequence: load_static_para(file) -> load_data -> forward_blu -> x_rec."""
+    m = models[qp]
+    anchor, ori = synth.make_frames(0xC0FFEE, 1, 240, 416)
+    path = tmp_path / ("qvrcnn_nchw_vect_c_8bit_qfp_%d.data" % qp)
+    path.write_bytes(formats.write_model_vect_c(m))
+    net = api.QVRCNN(0, 1, 1, 240, 416)
+    net.load_static_para(str(path))
+    _fused_or_skip(net, impl)
+    net.set_impl(impl)
+    net.load_data(anchor)
+    net.forward_blu()
+    rec = net.get_recon()
+    want = _oracle(m).forward_blu(anchor)
+    assert np.array_equal(rec, want), "mismatching pixels: %d" % int((rec != want).sum())
+    assert (rec != anchor).any()
+    if qp == 37:
+        gold = json.load(open(os.path.join(GOLDEN, "oracle_checksums.json")))["qp37_416x240"]
+        assert hashlib.sha256(rec.tobytes()).hexdigest() == gold
+    # identical frames => identical PSNR report
+    d = api.VRCNNData(1, 240, 416)
+    d.ori[:] = ori
+    from oracle import oracle
+    assert d.psnr(rec) == oracle.psnr(want, ori)[0]
+
+
+@pytest.mark.parametrize("qp", [22, 27, 32, 37])
+def test_layered_activations_match_oracle(models, qp):
+    """Per-layer parity: a1 / a2 / a3 (C1.v, Conc1.conc, Conc2.conc) vs the oracle's taps."""
+    m = models[qp]
+    anchor, _ = synth.make_frames(0xC0FFEE + 2, 1, 72, 104)
+    net = _net(m, 1, 72, 104, api.IMPL_LAYERED)
+    net.load_data(anchor)
+    net.forward_blu()
+    rec, a1, a2, a3, _ = _oracle(m).forward_taps(anchor[0])
+    assert np.array_equal(net.get_activation(1), a1)
+    assert np.array_equal(net.get_activation(2), a2)
+    assert np.array_equal(net.get_activation(3), a3)
+    assert np.array_equal(net.get_recon()[0], rec)
+
+
+@pytest.mark.parametrize("impl", IMPLS, ids=lambda i: IMPL_NAME[i])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (7, 5), (13, 13), (33, 31), (8, 257), (130, 20), (61, 123)])
+def test_ragged_and_tiny_frames(models, impl, shape):
+    """Frames smaller than one tile / not multiples of any tile size / thinner than the halo."""
+    m = models[32]
+    h, w = shape
+    x = synth.make_uniform_frames(17, 2, h, w)
+    net = _net(m, 2, h, w, api.IMPL_LAYERED)
+    _fused_or_skip(net, impl)
+    net.set_impl(impl)
+    net.load_data(x)
+    net.forward_blu()
+    assert np.array_equal(net.get_recon(), _oracle(m).forward_blu(x))
+
+
+@pytest.mark.parametrize("impl", IMPLS, ids=lambda i: IMPL_NAME[i])
+@pytest.mark.parametrize("value", [0, 128, 255])
+def test_constant_frames(models, impl, value):
+    m = models[27]
+    x = np.full((1, 40, 72), value, np.uint8)
+    net = _net(m, 1, 40, 72, api.IMPL_LAYERED)
+    _fused_or_skip(net, impl)
+    net.set_impl(impl)
+    net.load_data(x)
+    net.forward_blu()
+    assert np.array_equal(net.get_recon(), _oracle(m).forward_blu(x))
+
+
+@pytest.mark.parametrize("impl", IMPLS, ids=lambda i: IMPL_NAME[i])
+def test_config2_8x832x480_all_qps(models, impl):
+    """BASELINE config 2: 8-frame 832x480 sequence, all four QP sets; oracle on frames 0 and 7,
+    the other frames through frame-independence (batch result == per-frame result)."""
+    anchor, _ = synth.make_frames(0xC0FFEE + 3, 8, 480, 832)
+    for qp in (22, 27, 32, 37):
+        m = models[qp]
+        net = _net(m, 8, 480, 832, api.IMPL_LAYERED)
+        _fused_or_skip(net, impl)
+        net.set_impl(impl)
+        out = net.forward_frames_host(anchor)
+        om = _oracle(m)
+        assert np.array_equal(out[0], om.forward_blu(anchor[0:1])[0])
+        assert np.array_equal(out[7], om.forward_blu(anchor[7:8])[0])
+        one = _net(m, 1, 480, 832, impl)
+        for f in (3, 5):
+            one.load_data(anchor[f])
+            one.forward_blu()
+            assert np.array_equal(one.get_recon()[0], out[f])
+        net.close(); one.close()
+
+
+def test_fused_equals_layered_1080p(models):
+    """Full-size property check (BASELINE config 3 geometry, 6 of the 64 frames): two independently
+    written CUDA implementations agree bit for bit, and frame 0 also matches the oracle."""
+    m = models[32]
+    anchor, _ = synth.make_frames(0xC0FFEE + 4, 6, 1080, 1920)
+    a = _net(m, 6, 1080, 1920, api.IMPL_LAYERED)
+    out_l = a.forward_frames_host(anchor)
+    _fused_or_skip(a, api.IMPL_FUSED)
+    a.set_impl(api.IMPL_FUSED)
+    out_f = a.forward_frames_host(anchor)
+    assert np.array_equal(out_l, out_f)
+    assert np.array_equal(out_f[0], _oracle(m).forward_blu(anchor[0:1])[0])
+
+
+@pytest.mark.parametrize("impl", IMPLS, ids=lambda i: IMPL_NAME[i])
+def test_rows_mode_strips_equal_whole_frame(models, impl):
+    """Spatial partition (BASELINE config 5 in miniature): a frame cut into 3 horizontal strips with
+    6-row input halos reproduces the whole-frame result bit for bit."""
+    import torch
+    m = models[22]
+    h, w = 150, 200
+    anchor, _ = synth.make_frames(0xC0FFEE + 5, 1, h, w)
+    net = _net(m, 1, h, w, api.IMPL_LAYERED)
+    _fused_or_skip(net, impl)
+    net.set_impl(impl)
+    net.load_data(anchor)
+    net.forward_blu()
+    whole = net.get_recon()[0]
+    d_in = torch.from_numpy(anchor[0]).cuda()
+    d_out = torch.zeros_like(d_in)
+    bounds = [0, 47, 101, h]
+    for i in range(3):
+        y0, y1 = bounds[i], bounds[i + 1]
+        r0, r1 = max(0, y0 - 6), min(h, y1 + 6)
+        net.forward_rows_device(d_in.data_ptr() + r0 * w, h, r0, r1 - r0, d_out.data_ptr() + y0 * w, y0, y1)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), whole)
+    with pytest.raises(api.QVError):      # fewer than 6 halo rows on an interior edge is refused
+        net.forward_rows_device(d_in.data_ptr() + 45 * w, h, 45, 60, d_out.data_ptr() + 47 * w, 47, 101)
+
+
+def test_device_entry_and_sse(models):
+    """qv_forward_frames_device on torch-owned device memory + on-device exact SSE == host PSNR."""
+    import torch
+    m = models[37]
+    anchor, ori = synth.make_frames(0xC0FFEE + 6, 3, 64, 96)
+    net = _net(m, 2, 64, 96, api.IMPL_AUTO)          # n_frames (3) > batch (2): chunked
+    d_in = torch.from_numpy(anchor).cuda()
+    d_ori = torch.from_numpy(ori).cuda()
+    d_out = torch.empty_like(d_in)
+    acc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    net.forward_frames_device(d_in.data_ptr(), d_out.data_ptr(), 3, st)
+    api.sse_device(d_out.data_ptr(), d_ori.data_ptr(), d_in.numel(), acc.data_ptr(), st)
+    torch.cuda.synchronize()
+    rec = d_out.cpu().numpy()
+    want = _oracle(m).forward_blu(anchor)
+    assert np.array_equal(rec, want)
+    p, sse = formats.psnr(want, ori)
+    assert int(acc.item()) == sse
+    assert api.psnr_from_sse(int(acc.item()), rec.size) == pytest.approx(p, abs=1e-12)
+    assert net.launch_count() > 0
+
+
+def test_error_behaviour(models, tmp_path):
+    net = api.QVRCNN(0, 1, 1, 16, 16)
+    with pytest.raises(api.QVError) as e:           # forward before load
+        net.forward_blu()
+    assert e.value.code == -5
+    with pytest.raises(api.QVError) as e:           # the reference prints "cannot open model file." and exits
+        net.load_static_para(str(tmp_path / "missing.data"))
+    assert e.value.code == -2 and "cannot open model file" in str(e.value)
+    bad = tmp_path / "short.data"
+    bad.write_bytes(b"\0" * 100)
+    with pytest.raises(api.QVError):
+        net.load_static_para(str(bad))
+    with pytest.raises(api.QVError):
+        api.QVRCNN(0, 1, 3, 16, 16)                  # luma only
+    # outside the exact-integer envelope -> refused, not silently different
+    m = synth.make_model(1, 32)
+    m.w[2][...] = 127
+    with pytest.raises(api.QVError) as e:
+        net.load_static_para_mem(formats.write_model_vect_c(m))
+    assert e.value.code == -4
+
+
+def test_quant_param_file_plus_set_weights(models, tmp_path):
+    """The shipped artefact is the per-QP scale file; weights come separately."""
+    m = models[27]
+    q = tmp_path / "quant_params27.data"
+    formats.write_quant_params_pickle(str(q), formats.qparams_rows_from_table(27))
+    anchor, _ = synth.make_frames(3, 1, 32, 48)
+    net = api.QVRCNN(0, 1, 1, 32, 48)
+    net.load_quant_params(str(q))
+    for l in range(6):
+        net.set_weights(l, m.w[l], m.b[l])
+    assert net.quant_params().tolist() == [list(t) for t in formats.SHIPPED_QPARAMS[27]]
+    net.load_data(anchor)
+    net.forward_blu()
+    assert np.array_equal(net.get_recon(), _oracle(m).forward_blu(anchor))
