@@ -1,0 +1,255 @@
+#!/usr/bin/env python
+"""bench.py -- luma Mpixel/s of the QVRCNN int8 pass (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--kernel auto|fused|layered]
+
+A "step" is one pass of the hot path over one batch of synthetic luma: BASELINE config 3,
+QP=32, 64 frames of 1920x1080 per GPU (weak scaling: every rank processes its own 64 frames,
+frame-sharded, no data-path collective; the only collective is the int64 SSE all-reduce of the
+PSNR report, outside the timed region).  `value` = whole-job Mpixel/s with the frames already
+resident in HBM; `e2e` = the same metric through the host-buffer entry point
+qv_forward_frames_host (pinned host memory -> H2D -> net -> D2H every step).
+
+--impl reference times the reference path's CPU restatement (oracle/, the only CPU implementation
+of this path that exists: the reference itself is cuDNN-only) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_PIXEL = 109024          # 2 * 54512 MAC, BASELINE.md section 2
+HBM_BYTES_PER_PIXEL = 2          # 1 B luma in + 1 B recon out
+QP, FRAMES, H, W = 32, 64, 1080, 1920
+WORKLOAD = "config3: QVRCNN QP=32, 64x1920x1080 synthetic luma frames per GPU"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def build_inputs(rank: int):
+    from qcnn_gpu_b200.host import formats, synth
+    model = synth.make_model(0xC0FFEE + QP, QP)
+    uniq = 8                                    # 8 distinct frames per rank, repeated to 64
+    anchor, ori = synth.make_frames(0xC0FFEE + 3, uniq, H, W, first_frame=rank * uniq)
+    reps = FRAMES // uniq
+    return model, formats.write_model_vect_c(model), np.tile(anchor, (reps, 1, 1)), np.tile(ori, (reps, 1, 1))
+
+
+def run_reference(args, rank: int, world: int):
+    """CPU arm: the oracle (port of the reference's forward_blu) on all host threads; each step is a
+    bounded sample of the workload (one 1920x1080 frame of the same synthetic batch)."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    from qcnn_gpu_b200.host import formats, synth
+    model = synth.make_model(0xC0FFEE + QP, QP)
+    om = oracle.OracleModel(formats.write_model_vect_c(model))
+    anchor, _ = synth.make_frames(0xC0FFEE + 3, 1, H, W)
+    for _ in range(args.warmup):
+        om.forward_blu(anchor[:, :270])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        om.forward_blu(anchor)
+    dt = time.perf_counter() - t0
+    mpx = args.steps * H * W / dt / 1e6
+    cores = oracle.num_threads()
+    line = {"impl": "reference", "metric": "luma Mpixel/s (QVRCNN int8, 1080p)", "value": mpx, "unit": "Mpixel/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "one 1920x1080 frame of the batch per step"},
+            "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                             "sample": "%d x one 1920x1080 frame, OpenMP C oracle (oracle/qvrcnn_oracle.c)" % args.steps},
+            "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "fused", "layered"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 6:
+            args.steps = 6                      # bounded: ~3-4 s of CPU per 1080p frame
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from qcnn_gpu_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model, image, anchor, ori = build_inputs(rank)
+    net = api.QVRCNN(local, FRAMES, 1, H, W)
+    net.load_static_para_mem(image)
+    net.set_impl({"auto": api.IMPL_AUTO, "fused": api.IMPL_FUSED, "layered": api.IMPL_LAYERED}[args.kernel])
+    impl_name = {api.IMPL_FUSED: "fused-tcgen05", api.IMPL_LAYERED: "layered-dp4a"}[net.get_impl()]
+
+    h_in = torch.from_numpy(anchor).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    d_in = h_in.cuda()
+    d_ori = torch.from_numpy(ori).cuda()
+    d_out = torch.empty_like(d_in)
+    stream = torch.cuda.current_stream()
+    npx = FRAMES * H * W
+
+    def step_device():
+        net.forward_frames_device(d_in.data_ptr(), d_out.data_ptr(), FRAMES, stream.cuda_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = net.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step_device()
+        evs[i + 1].record(stream)
+    barrier()
+    launches = net.launch_count() - l0
+    sampler.stop_flag.set()
+    sampler.join()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+
+    # PSNR report + exact SSE (outside the timed region); the one collective of the job
+    acc = torch.zeros(2, dtype=torch.int64, device="cuda")
+    api.sse_device(d_in.data_ptr(), d_ori.data_ptr(), npx, acc[0:1].data_ptr(), stream.cuda_stream)
+    api.sse_device(d_out.data_ptr(), d_ori.data_ptr(), npx, acc[1:2].data_ptr(), stream.cuda_stream)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    torch.cuda.synchronize()
+    total_ms = float(tmax.item())
+    psnr_before = api.psnr_from_sse(int(acc[0].item()), npx * world)
+    psnr_after = api.psnr_from_sse(int(acc[1].item()), npx * world)
+
+    # end to end through the host-buffer entry point (pinned host memory in and out, every step)
+    for _ in range(2):
+        net.forward_frames_host_ptr(h_in.data_ptr(), h_out.data_ptr(), FRAMES)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        net.forward_frames_host_ptr(h_in.data_ptr(), h_out.data_ptr(), FRAMES)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_mpx = world * npx * e2e_steps / float(e2e_s.item()) / 1e6
+    same = bool(torch.equal(h_out.cuda(), d_out))
+
+    if rank == 0:
+        peaks = measured_peaks()
+        value = world * npx * args.steps / (total_ms * 1e-3) / 1e6
+        per_gpu_px_s = npx * args.steps / (total_ms * 1e-3)
+        tops = per_gpu_px_s * OPS_PER_PIXEL / 1e12
+        int8_peak = 2.0 * peaks["bf16_sustained"]
+        line = {
+            "metric": "luma Mpixel/s (QVRCNN int8, 1080p)", "value": value, "unit": "Mpixel/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "kernel": impl_name, "frames_per_gpu": FRAMES, "parallelism": "frame-sharded dp%d" % world,
+                       "l2": "inputs+outputs (265 MB/step) larger than L2 (126 MB)"},
+            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": npx, "d2h_bytes_per_step": npx,
+                    "api": "qv_forward_frames_host (pinned host in/out)", "bit_identical_to_device_path": same},
+            "roofline": {"bound": "tensor", "achieved": tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": tops / int8_peak,
+                         "traffic": None, "peak_source": "2 x bf16_tflops_sustained, " + peaks["source"],
+                         "frac_of_nominal_4500": tops / 4500.0,
+                         "hbm": {"achieved_gbs": per_gpu_px_s * HBM_BYTES_PER_PIXEL / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                                 "frac": per_gpu_px_s * HBM_BYTES_PER_PIXEL / 1e9 / peaks["hbm_gbs"]},
+                         "kernel_ms_per_launch": total_ms / max(1, launches)},
+            "clocks": sampler.summary(),
+            "psnr": {"before_net": psnr_before, "after_quantized_net": psnr_after},
+            "step_ms": [round(x, 3) for x in step_ms],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle
+            from qcnn_gpu_b200.host import formats
+            om = oracle.OracleModel(formats.write_model_vect_c(model))
+            om.forward_blu(anchor[:1, :135])
+            t0 = time.perf_counter()
+            nb = 4
+            ref = om.forward_blu(anchor[:nb])
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nb * H * W / dt / 1e6, "unit": "Mpixel/s", "cores": oracle.num_threads(), "kind": "port",
+                                    "sample": "%d of the 64 frames (1920x1080), OpenMP C oracle" % nb,
+                                    "gpu_matches_oracle_on_sample": bool(np.array_equal(ref, d_out[:nb].cpu().numpy()))}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
