@@ -205,6 +205,114 @@ static int run_thr()
     return 0;
 }
 
+
+// ---- throughput v2: unrolled issue loop, descriptors formed by one add of a constant -------
+// MODE 0: SS.  MODE 1: TS.  MODE 2: tcgen05.cp.128x256b only.  MODE 3: L2-like mix for one output
+// row (18 x N=48 + 32 x N=16, SS).  MODE 4: TMEM-A mix: 10 cp + (18 x N=48 + 32 x N=16) TS.
+template <int N, int MODE>
+__global__ void k_thr2(int outer, long long *cycles, int *status)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sA = sm;                            // 2 planes x 1024 px x 16 B = 32 KB
+    uint8_t *sB = sm + 32768;                    // 8 KB
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (32768 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sm)[i] = 0x01010101u * (i & 3);
+    fence_proxy_async_smem();
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = s_tmem;
+    if (tid == 0) {
+        constexpr uint32_t id = idesc_i8(128, N, 1, 1), id48 = idesc_i8(128, 48, 1, 1), id16 = idesc_i8(128, 16, 1, 1);
+        const uint64_t bd = smem_desc(smem_u32(sB), N * 16, 128);
+        const uint64_t bd48 = smem_desc(smem_u32(sB), 48 * 16, 128), bd16 = smem_desc(smem_u32(sB), 16 * 16, 128);
+        const uint64_t ad0 = smem_desc(smem_u32(sA), 16384, 128);
+        long long t0 = clock64();
+        for (int o = 0; o < outer; ++o) {
+            if (MODE == 0 || MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t acc = (j > 0) ? 1u : (o > 0);
+                    if (MODE == 0) mma_i8_ss(tm, ad0 + (uint64_t)((j * 37) % 800), bd, id, acc);
+                    else mma_i8_ts(tm, tm + 256 + (j & 7) * 8, bd, id, acc);
+                }
+            } else if (MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tm + 256 + (j & 15) * 8), "l"(ad0 + (uint64_t)((j * 37) % 800)) : "memory");
+            } else {
+                if (MODE == 4) {
+#pragma unroll
+                    for (int j = 0; j < 10; ++j)
+                        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tm + 256 + j * 8), "l"(ad0 + (uint64_t)((j * 37) % 800)) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 50; ++j) {
+                    const bool inner = j < 18;
+                    const uint32_t acc = (j > 0) ? 1u : (o > 0);
+                    const uint32_t d = inner ? tm : tm + 0;     // outer taps target the first 16 columns
+                    if (MODE == 3) mma_i8_ss(d, ad0 + (uint64_t)((j * 37) % 800), inner ? bd48 : bd16, inner ? id48 : id16, acc);
+                    else mma_i8_ts(d, tm + 256 + (j & 31) * 8, inner ? bd48 : bd16, inner ? id48 : id16, acc);
+                }
+            }
+        }
+        long long t1 = clock64();
+        mma_commit(&bar);
+        const bool ok = mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        cycles[0] = t1 - t0;
+        cycles[1] = t2 - t0;
+        status[0] = ok ? 0 : 1;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+template <int N, int MODE>
+static void thr2_case(const char *name, long long *dC, int *dSt)
+{
+    CK(cudaFuncSetAttribute(k_thr2<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8192));
+    const int outer = 64;
+    for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaMemset(dSt, 0, 4));
+        k_thr2<N, MODE><<<1, 128, 32768 + 8192>>>(outer, dC, dSt);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("thr2 %s N=%d: CUDA error %s\n", name, N, cudaGetErrorString(e)); exit(2); }
+    }
+    long long c[2]; int st;
+    CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost));
+    if (MODE <= 1) {
+        const double per = (double)c[1] / (outer * 32);
+        printf("thr2 %-3s M=128 N=%3d : issue %.1f, complete %.1f cyc/mma -> %.0f MAC/clk/SM (math floor %.1f, smem bytes/clk %.0f) timeout=%d\n", name, N,
+               (double)c[0] / (outer * 32), per, 128.0 * N * 32 / per, N / 2.0, (MODE == 0 ? 4096.0 + 32.0 * N : 32.0 * N) / per, st);
+    } else if (MODE == 2) {
+        const double per = (double)c[1] / (outer * 32);
+        printf("thr2 cp.128x256b : issue %.1f, complete %.1f cyc/copy -> %.0f B/clk timeout=%d\n", (double)c[0] / (outer * 32), per, 4096.0 / per, st);
+    } else {
+        const double per = (double)c[1] / outer;
+        printf("thr2 %s : %.0f cyc per layer-2 row (50 MMAs%s); ideal math 688; issue %.0f  timeout=%d\n", name, per, MODE == 4 ? " + 10 cp" : "", (double)c[0] / outer, st);
+    }
+}
+
+static int run_thr2()
+{
+    long long *dC; int *dSt;
+    CK(cudaMalloc(&dC, 16)); CK(cudaMalloc(&dSt, 4));
+    thr2_case<8, 0>("SS", dC, dSt);   thr2_case<16, 0>("SS", dC, dSt);  thr2_case<32, 0>("SS", dC, dSt);  thr2_case<48, 0>("SS", dC, dSt);
+    thr2_case<64, 0>("SS", dC, dSt);  thr2_case<96, 0>("SS", dC, dSt);  thr2_case<128, 0>("SS", dC, dSt); thr2_case<256, 0>("SS", dC, dSt);
+    thr2_case<8, 1>("TS", dC, dSt);   thr2_case<16, 1>("TS", dC, dSt);  thr2_case<32, 1>("TS", dC, dSt);  thr2_case<48, 1>("TS", dC, dSt);
+    thr2_case<64, 1>("TS", dC, dSt);  thr2_case<96, 1>("TS", dC, dSt);  thr2_case<128, 1>("TS", dC, dSt); thr2_case<256, 1>("TS", dC, dSt);
+    thr2_case<16, 2>("cp", dC, dSt);
+    thr2_case<16, 3>("L2-mix SS", dC, dSt);
+    thr2_case<16, 4>("L2-mix TS+cp", dC, dSt);
+    return 0;
+}
+
 // ---- A from TMEM: tcgen05.st layout hypothesis and tcgen05.cp ---------------------------
 // variant 0: A written by tcgen05.st (lane m, column j = bytes k=4j..4j+3 little endian)
 // variant 1: A copied by tcgen05.cp.128x256b from the smem K-major no-swizzle layout
@@ -444,6 +552,7 @@ int main(int argc, char **argv)
     printf("# %s  sm_%d%d  %d SMs  clock %d MHz   test=%s\n", p.name, p.major, p.minor, p.multiProcessorCount, p.clockRate / 1000, t);
     if (!strcmp(t, "num")) return run_num();
     if (!strcmp(t, "thr")) return run_thr();
+    if (!strcmp(t, "thr2")) return run_thr2();
     if (!strcmp(t, "ts")) return run_ts();
     if (!strcmp(t, "ldst")) return run_ldst();
     if (!strcmp(t, "shift")) return run_shift();
