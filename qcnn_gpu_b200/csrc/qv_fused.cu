@@ -22,6 +22,7 @@
 // mma_done -> workers may read D*[i&1] and overwrite the smem rows iteration i read).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -84,6 +85,7 @@ struct FusedParams {
     GroupQ q1, q22, q21, q31, q32;
     int c4_bias, c4_mul, c4_shift;
     int c4_w[108];                     // [tap][plane][4 words], 4 channels per word
+    long long *dbg;                    // optional per-block phase timers (QV_FUSED_PROFILE=1), else null
 };
 
 __device__ __forceinline__ int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
@@ -121,10 +123,13 @@ template <bool FAST>
 __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ FusedParams P)
 {
     extern __shared__ __align__(1024) uint8_t sm[];
-    uint64_t *bar_work = reinterpret_cast<uint64_t *>(sm + OFF_CTRL);
-    uint64_t *bar_mma = bar_work + 1;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(sm + OFF_CTRL + 16);
-    int *s_fail = reinterpret_cast<int *>(sm + OFF_CTRL + 24);
+    // Two mbarriers per direction, used alternately (event e -> barrier e&1, parity (e>>1)&1): a
+    // waiter can then never be lapped, because the second-next completion of the SAME barrier
+    // needs the waiter's own arrival in between.
+    uint64_t *bar_work = reinterpret_cast<uint64_t *>(sm + OFF_CTRL);        // [2] workers -> MMA
+    uint64_t *bar_mma = bar_work + 2;                                        // [2] MMA (tcgen05.commit) -> workers
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(sm + OFF_CTRL + 32);
+    int *s_fail = reinterpret_cast<int *>(sm + OFF_CTRL + 36);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = P.H, W = P.W;
 
@@ -134,8 +139,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     for (int i = tid; i < (OFF_CTRL - OFF_A1) / 16; i += NTHREADS)      // finite data everywhere the MMAs may read
         reinterpret_cast<uint4 *>(sm + OFF_A1)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        mbar_init(bar_work, 8);
-        mbar_init(bar_mma, 1);
+        mbar_init(&bar_work[0], 8);
+        mbar_init(&bar_work[1], 8);
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
         *s_fail = 0;
         mbar_fence_init();
     }
@@ -149,8 +156,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
 
     if (warp == 8) {
         // =============================== MMA issuer ========================================
-        if (lane == 0) {
-            uint32_t ph_work = 0;
+        // The whole warp runs the control flow (so that descriptors stay in uniform registers);
+        // one elected lane issues the tcgen05 instructions.
+        const bool leader = elect_one();
+        {
+            uint32_t ev_work = 0, ev_mma = 0;
+            long long t_wait = 0, t_issue = 0, tc0 = clock64();
             constexpr uint32_t ID64 = idesc_i8(128, 64), ID48 = idesc_i8(128, 48), ID16 = idesc_i8(128, 16);
             constexpr uint32_t HI_A = (128u >> 4) | (1u << 14);                 // SBO = 128 B, version 1
             const uint32_t a_lo_plane = (uint32_t)PW16 << 16;                    // LBO = one plane
@@ -160,18 +171,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             const uint32_t w3_lo48 = ((sbase + OFF_W3) >> 4) | ((48u * 16 >> 4) << 16);
             const uint32_t w3_lo16 = ((sbase + OFF_W3 + 2 * W3_BIG) >> 4) | ((16u * 16 >> 4) << 16);
             auto desc = [](uint32_t lo) { return ((uint64_t)HI_A << 32) | lo; };
+            auto MMA = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+                if (leader) mma_i8_ss(d, a, b, idesc, acc);
+            };
             for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
                 const int seg = unit % P.nseg;
                 const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
                 const int niter = y1 - y0 + PIPE;
                 for (int i = 0; i < niter; ++i) {
                     const int R1 = y0 - 4 + i;
-                    if (!mbar_wait(bar_work, ph_work)) { *s_fail = 1; }
-                    ph_work ^= 1;
+                    if (!mbar_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1)) { *s_fail = 1; }
+                    ++ev_work;
                     fence_after_sync();
+                    { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
                     const uint32_t par = i & 1;
                     // ---- L1: a1 row R1 = im2col[par] x W1 -------------------------------------
-                    mma_i8_ss(tm + TM_D1 + par * 64, desc((((sbase + OFF_IM + par * IM_BYTES) >> 4)) | ((128u * 16 >> 4) << 16)),
+                    MMA(tm + TM_D1 + par * 64, desc((((sbase + OFF_IM + par * IM_BYTES) >> 4)) | ((128u * 16 >> 4) << 16)),
                               desc(w1_lo), ID64, 0);
                     // ---- L2: a2 row R2 = R1-4 from a1 rows R2-2..R2+2 ---------------------------
                     {
@@ -186,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 const int r = 1 + t / 3, s = 1 + t % 3;
-                                mma_i8_ss(d2, desc(row16[r] + h * 2 * PW16 + 4 + s),
+                                MMA(d2, desc(row16[r] + h * 2 * PW16 + 4 + s),
                                           desc(w2_lo48 + ((t * 2 + h) * W2_INNER >> 4)), ID48, (t | h) != 0);
                             }
                         // outer ring of the 5x5: N = 16 (C2_2 only, columns 0..15)
@@ -197,7 +212,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                             if (r >= 1 && r <= 3 && s >= 1 && s <= 3) continue;
 #pragma unroll
                             for (int h = 0; h < 2; ++h)
-                                mma_i8_ss(d2, desc(row16[r] + h * 2 * PW16 + 4 + s),
+                                MMA(d2, desc(row16[r] + h * 2 * PW16 + 4 + s),
                                           desc(w2_lo16 + ((oi * 2 + h) * W2_OUTER >> 4)), ID16, 1);
                             ++oi;
                         }
@@ -211,8 +226,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         const uint32_t d3 = tm + TM_D3 + par * 48;
                         const uint32_t lbo_px = 1u << 16;                       // LBO = 16 B: next pixel, same plane
                         // the two K-steps that contain the centre tap carry C3_2 as well: N = 48
-                        mma_i8_ss(d3, desc((row16[1] + 6 + 1) | a_lo_plane), desc(w3_lo48), ID48, 0);
-                        mma_i8_ss(d3, desc((row16[1] + 2 * PW16 + 6 + 0) | lbo_px), desc(w3_lo48 + (W3_BIG >> 4)), ID48, 1);
+                        MMA(d3, desc((row16[1] + 6 + 1) | a_lo_plane), desc(w3_lo48), ID48, 0);
+                        MMA(d3, desc((row16[1] + 2 * PW16 + 6 + 0) | lbo_px), desc(w3_lo48 + (W3_BIG >> 4)), ID48, 1);
                         int bi = 0;
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
@@ -223,14 +238,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                                 if (k < 3) a = (row16[r] + 6 + k) | a_lo_plane;                  // (s=k : planes 0,1)
                                 else if (k == 3) a = (row16[r] + 2 * PW16 + 6 + 0) | lbo_px;     // (s0 plane2 | s1 plane2)
                                 else a = (row16[r] + 2 * PW16 + 6 + 2) | lbo_px;                 // (s2 plane2 | zero weights)
-                                mma_i8_ss(d3, desc(a), desc(w3_lo16 + (bi * W3_SMALL >> 4)), ID16, 1);
+                                MMA(d3, desc(a), desc(w3_lo16 + (bi * W3_SMALL >> 4)), ID16, 1);
                                 ++bi;
                             }
                         }
                     }
-                    mma_commit(bar_mma);
+                    if (leader) mma_commit(&bar_mma[ev_mma & 1]);
+                    ++ev_mma;
+                    __syncwarp();
+                    { const long long t = clock64(); t_issue += t - tc0; tc0 = t; }
                 }
             }
+            if (P.dbg && leader) { P.dbg[blockIdx.x * 16 + 0] = t_wait; P.dbg[blockIdx.x * 16 + 1] = t_issue; }
         }
     } else {
         // ================================= workers =========================================
@@ -238,7 +257,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         const int m = q * 32 + lane;                              // this thread's MMA row / pixel
         const uint32_t tm_lane = tm + ((uint32_t)(q * 32) << 16);
         const int *s_bias = reinterpret_cast<const int *>(sm + OFF_BIAS);
-        uint32_t ph_mma = 0;
+        uint32_t ev_work = 0, ev_mma = 0;
+        long long tw[6] = {0, 0, 0, 0, 0, 0}, tc0 = clock64();
+        auto lap = [&](int k) { const long long t = clock64(); tw[k] += t - tc0; tc0 = t; };
         auto worker_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
@@ -281,15 +302,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 if (hh == 1) im2col(R1, 0);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_work);
+                if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+                ++ev_work;
             }
             for (int i = 0; i < niter; ++i) {
                 const int R1 = y0 - 4 + i;
                 const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
                 if (i >= 1) {
-                    if (!mbar_wait(bar_mma, ph_mma)) { *s_fail = 1; }
-                    ph_mma ^= 1;
+                    if (!mbar_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1)) { *s_fail = 1; }
+                    ++ev_mma;
                     fence_after_sync();
+                    lap(0);
                     const uint32_t par = (i - 1) & 1;
                     // ---- epilogue 1: a1 row R1-1, 64 channels = 4 groups; hh picks two of them ------
                     {
@@ -344,15 +367,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         }
                     }
                 }
+                lap(1);
                 if (i + 1 < niter) {
                     if (hh == 1) im2col(R1 + 1, (i + 1) & 1);
                     fence_proxy_async_smem();                     // st.shared above -> visible to the tensor core
                     fence_before_sync();                          // tcgen05.ld above ordered before the MMAs that overwrite D
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_work);
+                    if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+                    ++ev_work;
                 }
+                lap(2);
                 store_in(R1 + 4, in_next);
                 worker_bar();                                     // a3 row + input ring visible to every worker
+                lap(3);
                 // ---- C4 (48 -> 1, 3x3) + applyRes_y for output row R1-9 (cnn.cu:507-523) -----------
                 const int R4 = R1 - 9;
                 if (hh == 0 && R4 >= y0 && R4 < y1 && m < WT && X0 + m < W) {
@@ -375,13 +402,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     const int x = sm[OFF_IN + mod_pos(R4, IN_SLOTS) * IN_PITCH + 8 + m];
                     outf[(size_t)R4 * W + X0 + m] = (uint8_t)residual_apply(acc + P.c4_bias, x, P.c4_mul, P.c4_shift);
                 }
+                lap(4);
             }
             // drain: the MMAs of the last iteration still read smem / write TMEM
-            if (!mbar_wait(bar_mma, ph_mma)) { *s_fail = 1; }
-            ph_mma ^= 1;
+            if (!mbar_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1)) { *s_fail = 1; }
+            ++ev_mma;
             fence_after_sync();
             worker_bar();
+            lap(5);
         }
+        if (P.dbg && (tid == 0 || tid == 128))
+            for (int k = 0; k < 6; ++k) P.dbg[blockIdx.x * 16 + 2 + (tid >> 7) * 6 + k] = tw[k];
     }
     fence_before_sync();
     __syncthreads();
@@ -553,10 +584,29 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     if (units > 0x7fffffffll) return cudaErrorInvalidValue;
     P.n_units = (int)units;
     const int grid = (int)std::min<long long>(units, fm->sm_count);
+    const bool prof = getenv("QV_FUSED_PROFILE") != nullptr;
+    P.dbg = nullptr;
+    if (prof && cudaMalloc(&P.dbg, (size_t)grid * 16 * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
+    if (P.dbg) cudaMemsetAsync(P.dbg, 0, (size_t)grid * 16 * sizeof(long long), st);
     if (fm->fast) k_fused<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     else k_fused<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     if (launches) *launches += 1;
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (P.dbg) {
+        std::vector<long long> h((size_t)grid * 16);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), P.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(P.dbg);
+        double a[14] = {0};
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 14; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
+        const double iters = (double)P.n_units / grid * (P.seg_rows + PIPE);
+        fprintf(stderr, "[qv fused profile] units=%d grid=%d iters/block~%.0f | cycles per iteration: MMA warp wait=%.0f issue=%.0f | "
+                "worker w0 (C4 side): wait_mma=%.0f epi=%.0f im2col+arrive=%.0f bar=%.0f c4=%.0f drain=%.0f | "
+                "worker w4 (im2col side): wait_mma=%.0f epi=%.0f im2col+arrive=%.0f bar=%.0f c4=%.0f drain=%.0f\n",
+                P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[4] / iters, a[5] / iters, a[6] / iters,
+                a[7] / iters, a[8] / iters, a[9] / iters, a[10] / iters, a[11] / iters, a[12] / iters, a[13] / iters);
+    }
+    return e;
 }
 
 }  // namespace qv
