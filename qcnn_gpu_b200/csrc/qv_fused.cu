@@ -61,7 +61,8 @@ constexpr int OFF_A2 = OFF_A1 + A1_SLOTS * A1_ROW;
 constexpr int OFF_A3 = OFF_A2 + A2_SLOTS * A2_ROW;
 constexpr int OFF_IM = OFF_A3 + A3_SLOTS * A3_ROW;
 constexpr int OFF_IN = OFF_IM + 2 * IM_BYTES;
-constexpr int OFF_CTRL = OFF_IN + IN_SLOTS * IN_PITCH;
+constexpr int OFF_PART = OFF_IN + IN_SLOTS * IN_PITCH;     // C4 partial sums, 128 ints
+constexpr int OFF_CTRL = OFF_PART + 512;
 constexpr int SMEM_BYTES = OFF_CTRL + 64;
 
 constexpr int NWORKER = 256, NTHREADS = NWORKER + 32;
@@ -73,7 +74,7 @@ constexpr int TM_D1 = 0, TM_D2 = 128, TM_D3 = 224, TM_COLS = 512;
 // Per 16-column accumulator group: everything the requantiser needs.
 struct GroupQ {
     int hi;          // FAST: blu + rbias          (upper clamp of acc + bias')
-    unsigned M;      // FAST: mul << (32 - shift)  (q = umulhi(t, M))
+    unsigned M;      // FAST: mul << (24 - shift)  (q = byte 3 of t * M)
     int blu, mul, shift, rbias;   // generic path: the reference formula verbatim
 };
 
@@ -106,17 +107,36 @@ __device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const int
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (FAST) {
-                // clamp(acc + b + rbias, 0, blu + rbias) * mul >> shift ; see DESIGN.md "epilogue"
+                // t = clamp(acc + b + rbias, 0, blu + rbias);  t * (mul << (24-shift)) < 2^31 and its top
+                // byte is (t * mul) >> shift  -- see DESIGN.md "epilogue arithmetic"
                 const unsigned t = (unsigned)__viaddmin_s32_relu((int)r[4 * v + j], bb[j], g.hi);
-                q[j] = __umulhi(t, Mz);
+                q[j] = t * Mz;
             } else {
                 QParam qp{g.blu, g.mul, g.shift, g.rbias};
-                q[j] = valid ? ((unsigned)blu_requant((int)r[4 * v + j] + bb[j], qp) & 0xffu) : 0u;
+                q[j] = valid ? ((unsigned)blu_requant((int)r[4 * v + j] + bb[j], qp) << 24) : 0u;
             }
         }
-        o[v] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+        // gather the four top bytes into one word
+        o[v] = __byte_perm(__byte_perm(q[0], q[1], 0x0073), __byte_perm(q[2], q[3], 0x0073), 0x5410);
     }
     *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// Partial C4 dot product of one pixel over (tap, plane) units [U0, U0+NU): 16 channels per unit.
+template <int U0, int NU>
+__device__ __forceinline__ int c4_partial(const uint8_t *px, const int (&slot3)[3], const FusedParams &P)
+{
+    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll
+    for (int u = U0; u < U0 + NU; ++u) {
+        const int t = u / 3, pl = u % 3, r = t / 3, sft = t % 3;
+        const uint4 v = *reinterpret_cast<const uint4 *>(px + slot3[r] + pl * PLANE + sft * 16);
+        acc0 = __dp4a((int)v.x, P.c4_w[u * 4 + 0], acc0);
+        acc1 = __dp4a((int)v.y, P.c4_w[u * 4 + 1], acc1);
+        acc2 = __dp4a((int)v.z, P.c4_w[u * 4 + 2], acc2);
+        acc3 = __dp4a((int)v.w, P.c4_w[u * 4 + 3], acc3);
+    }
+    return (acc0 + acc1) + (acc2 + acc3);
 }
 
 template <bool FAST>
@@ -314,56 +334,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     fence_after_sync();
                     lap(0);
                     const uint32_t par = (i - 1) & 1;
-                    // ---- epilogue 1: a1 row R1-1, 64 channels = 4 groups; hh picks two of them ------
+                    // ---- epilogues: a1 row R1-1 (D1, 4 groups), a2 row R1-5 (D2: group 0 = C2_2 -> plane 2,
+                    //      groups 1,2 = C2_1 -> planes 0,1), a3 row R1-8 (D3: group 0 = C3_1, 1,2 = C3_2).
+                    //      Each warp half (hh) takes 5 of the 10 sixteen-column groups; all TMEM loads first.
                     {
-                        const int row = R1 - 1, col = X0 - 4 + m;
-                        const bool valid = row >= 0 && row < H && col >= 0 && col < W;
-                        uint8_t *dst = sm + OFF_A1 + mod_pos(row, A1_SLOTS) * A1_ROW + (4 + m) * 16;
-                        uint32_t r0[16], r1[16];
-                        tmem_ld_x16(tm_lane + TM_D1 + par * 64 + (2 * hh) * 16, r0);
-                        tmem_ld_x16(tm_lane + TM_D1 + par * 64 + (2 * hh + 1) * 16, r1);
-                        tmem_ld_wait();
-                        requant_store<FAST>(r0, s_bias + (2 * hh) * 16, P.q1, valid, dst + (2 * hh) * PLANE);
-                        requant_store<FAST>(r1, s_bias + (2 * hh + 1) * 16, P.q1, valid, dst + (2 * hh + 1) * PLANE);
-                    }
-                    // ---- epilogue 2: a2 row R1-5; D2 groups: 0 = C2_2 -> plane 2, 1,2 = C2_1 -> planes 0,1
-                    {
-                        const int row = R1 - 5, col = X0 - 2 + m;
-                        const bool valid = row >= 0 && row < H && col >= 0 && col < W;
-                        uint8_t *dst = sm + OFF_A2 + mod_pos(row, A2_SLOTS) * A2_ROW + (6 + m) * 16;
-                        const uint32_t d2 = tm_lane + TM_D2 + par * 48;
-                        uint32_t r0[16];
+                        const int row1 = R1 - 1, row2 = R1 - 5, row3 = R1 - 8;
+                        const bool v1 = row1 >= 0 && row1 < H && X0 - 4 + m >= 0 && X0 - 4 + m < W;
+                        const bool v2 = row2 >= 0 && row2 < H && X0 - 2 + m >= 0 && X0 - 2 + m < W;
+                        const bool v3 = row3 >= 0 && row3 < H && X0 - 1 + m >= 0 && X0 - 1 + m < W;
+                        uint8_t *dst1 = sm + OFF_A1 + mod_pos(row1, A1_SLOTS) * A1_ROW + (4 + m) * 16;
+                        uint8_t *dst2 = sm + OFF_A2 + mod_pos(row2, A2_SLOTS) * A2_ROW + (6 + m) * 16;
+                        uint8_t *dst3 = sm + OFF_A3 + mod_pos(row3, A3_SLOTS) * A3_ROW + (7 + m) * 16;
+                        const uint32_t d1 = tm_lane + TM_D1 + par * 64, d2 = tm_lane + TM_D2 + par * 48, d3 = tm_lane + TM_D3 + par * 48;
+                        uint32_t ra[16], rb[16], rc[16], rd[16], re[16];
                         if (hh == 0) {
-                            uint32_t r1[16];
-                            tmem_ld_x16(d2 + 0, r0);
-                            tmem_ld_x16(d2 + 16, r1);
+                            tmem_ld_x16(d1 + 0, ra); tmem_ld_x16(d1 + 16, rb);
+                            tmem_ld_x16(d2 + 0, rc); tmem_ld_x16(d2 + 16, rd);
+                            tmem_ld_x16(d3 + 0, re);
                             tmem_ld_wait();
-                            requant_store<FAST>(r0, s_bias + 64 + 0, P.q22, valid, dst + 2 * PLANE);
-                            requant_store<FAST>(r1, s_bias + 64 + 16, P.q21, valid, dst + 0 * PLANE);
+                            requant_store<FAST>(ra, s_bias + 0, P.q1, v1, dst1 + 0 * PLANE);
+                            requant_store<FAST>(rb, s_bias + 16, P.q1, v1, dst1 + 1 * PLANE);
+                            requant_store<FAST>(rc, s_bias + 64 + 0, P.q22, v2, dst2 + 2 * PLANE);
+                            requant_store<FAST>(rd, s_bias + 64 + 16, P.q21, v2, dst2 + 0 * PLANE);
+                            requant_store<FAST>(re, s_bias + 112 + 0, P.q31, v3, dst3 + 0 * PLANE);
                         } else {
-                            tmem_ld_x16(d2 + 32, r0);
+                            tmem_ld_x16(d1 + 32, ra); tmem_ld_x16(d1 + 48, rb);
+                            tmem_ld_x16(d2 + 32, rc);
+                            tmem_ld_x16(d3 + 16, rd); tmem_ld_x16(d3 + 32, re);
                             tmem_ld_wait();
-                            requant_store<FAST>(r0, s_bias + 64 + 32, P.q21, valid, dst + 1 * PLANE);
-                        }
-                    }
-                    // ---- epilogue 3: a3 row R1-8; D3 groups: 0 = C3_1 -> plane 0, 1,2 = C3_2 -> planes 1,2
-                    {
-                        const int row = R1 - 8, col = X0 - 1 + m;
-                        const bool valid = row >= 0 && row < H && col >= 0 && col < W;
-                        uint8_t *dst = sm + OFF_A3 + mod_pos(row, A3_SLOTS) * A3_ROW + (7 + m) * 16;
-                        const uint32_t d3 = tm_lane + TM_D3 + par * 48;
-                        uint32_t r0[16];
-                        if (hh == 0) {
-                            tmem_ld_x16(d3 + 0, r0);
-                            tmem_ld_wait();
-                            requant_store<FAST>(r0, s_bias + 112 + 0, P.q31, valid, dst + 0 * PLANE);
-                        } else {
-                            uint32_t r1[16];
-                            tmem_ld_x16(d3 + 16, r0);
-                            tmem_ld_x16(d3 + 32, r1);
-                            tmem_ld_wait();
-                            requant_store<FAST>(r0, s_bias + 112 + 16, P.q32, valid, dst + 1 * PLANE);
-                            requant_store<FAST>(r1, s_bias + 112 + 32, P.q32, valid, dst + 2 * PLANE);
+                            requant_store<FAST>(ra, s_bias + 32, P.q1, v1, dst1 + 2 * PLANE);
+                            requant_store<FAST>(rb, s_bias + 48, P.q1, v1, dst1 + 3 * PLANE);
+                            requant_store<FAST>(rc, s_bias + 64 + 32, P.q21, v2, dst2 + 1 * PLANE);
+                            requant_store<FAST>(rd, s_bias + 112 + 16, P.q32, v3, dst3 + 1 * PLANE);
+                            requant_store<FAST>(re, s_bias + 112 + 32, P.q32, v3, dst3 + 2 * PLANE);
                         }
                     }
                 }
@@ -380,27 +383,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 store_in(R1 + 4, in_next);
                 worker_bar();                                     // a3 row + input ring visible to every worker
                 lap(3);
-                // ---- C4 (48 -> 1, 3x3) + applyRes_y for output row R1-9 (cnn.cu:507-523) -----------
+                // ---- C4 (48 -> 1, 3x3) + applyRes_y for output row R1-9 (cnn.cu:507-523).  The 27 (tap, plane)
+                //      units of a pixel are split 13 / 14 between the two warp halves; partial sums meet in smem.
                 const int R4 = R1 - 9;
-                if (hh == 0 && R4 >= y0 && R4 < y1 && m < WT && X0 + m < W) {
-                    int acc = 0;
+                if (R4 >= y0 && R4 < y1) {
+                    const uint8_t *px = sm + OFF_A3 + (7 + m) * 16;
+                    int slot3[3];
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const uint8_t *rowp = sm + OFF_A3 + mod_pos(R4 - 1 + r, A3_SLOTS) * A3_ROW + (7 + m) * 16;
-#pragma unroll
-                        for (int s = 0; s < 3; ++s)
-#pragma unroll
-                            for (int pl = 0; pl < 3; ++pl) {
-                                const uint4 v = *reinterpret_cast<const uint4 *>(rowp + pl * PLANE + s * 16);
-                                const int *w = &P.c4_w[((r * 3 + s) * 3 + pl) * 4];
-                                acc = __dp4a((int)v.x, w[0], acc);
-                                acc = __dp4a((int)v.y, w[1], acc);
-                                acc = __dp4a((int)v.z, w[2], acc);
-                                acc = __dp4a((int)v.w, w[3], acc);
-                            }
+                    for (int r = 0; r < 3; ++r) slot3[r] = mod_pos(R4 - 1 + r, A3_SLOTS) * A3_ROW;
+                    const int part = hh == 0 ? c4_partial<0, 13>(px, slot3, P) : c4_partial<13, 14>(px, slot3, P);
+                    int *s_part = reinterpret_cast<int *>(sm + OFF_PART);
+                    if (hh == 1) s_part[m] = part;
+                    worker_bar();
+                    if (hh == 0 && m < WT && X0 + m < W) {
+                        const int x = sm[OFF_IN + mod_pos(R4, IN_SLOTS) * IN_PITCH + 8 + m];
+                        outf[(size_t)R4 * W + X0 + m] =
+                            (uint8_t)residual_apply(part + s_part[m] + P.c4_bias, x, P.c4_mul, P.c4_shift);
                     }
-                    const int x = sm[OFF_IN + mod_pos(R4, IN_SLOTS) * IN_PITCH + 8 + m];
-                    outf[(size_t)R4 * W + X0 + m] = (uint8_t)residual_apply(acc + P.c4_bias, x, P.c4_mul, P.c4_shift);
                 }
                 lap(4);
             }
@@ -513,8 +512,8 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
         g.blu = L.blu; g.mul = L.mul; g.shift = L.shift; g.rbias = (1 << (L.shift - 1)) / L.mul;
         g.hi = L.blu + g.rbias;
         const long long top = ((long long)L.blu + g.rbias) * L.mul;
-        const bool ok = L.mul < (1ll << L.shift) && top < (1ll << 31) && (top >> L.shift) == 127 && g.hi < (1 << 30);
-        g.M = ok ? (unsigned)((unsigned long long)L.mul << (32 - L.shift)) : 0u;
+        const bool ok = L.shift <= 24 && L.mul < (1ll << L.shift) && top < (1ll << 31) && (top >> L.shift) == 127 && g.hi < (1 << 30);
+        g.M = ok ? (unsigned)((unsigned long long)L.mul << (24 - L.shift)) : 0u;
         return ok;
     };
     FusedParams &P = fm->proto;
