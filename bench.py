@@ -84,31 +84,76 @@ def build_inputs(rank: int):
     return model, formats.write_model_vect_c(model), np.tile(anchor, (reps, 1, 1)), np.tile(ori, (reps, 1, 1))
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "qcnn_ref_witness")
+
+
+def _gpu_present() -> bool:
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, timeout=20).returncode == 0
+    except Exception:
+        return False
+
+
 def run_reference(args, rank: int, world: int):
-    """CPU arm: the oracle (port of the reference's forward_blu) on all host threads; each step is a
-    bounded sample of the workload (one 1920x1080 frame of the same synthetic batch)."""
+    """Reference arm.  The reference has NO CPU implementation of this path: its forward_blu is six
+    cudnnConvolutionForward calls plus glue kernels (inference/cnn.cu:145-160).  When the witness binary
+    (the reference's own unmodified sources compiled against cuDNN by oracle/ref_witness/Makefile) and a GPU
+    are present, this arm runs THAT, with the reference's own driver sequence and timer scope (one frame at a
+    time on device 0: H2D, forward_blu, sync, D2H -- inference/kernel.cu:89-101), kind = "reference".
+    The CPU restatement (oracle port, all host threads) is timed beside it as `cpu_baseline`; it is also
+    the fallback `value` when the binary or the GPU is missing (kind = "port").  Each step is a bounded
+    sample of the workload: `sample_frames` 1920x1080 frames of the same synthetic batch."""
     if rank != 0:
         return
+    import tempfile
     from oracle import oracle
     from qcnn_gpu_b200.host import formats, synth
     model = synth.make_model(0xC0FFEE + QP, QP)
-    om = oracle.OracleModel(formats.write_model_vect_c(model))
-    anchor, _ = synth.make_frames(0xC0FFEE + 3, 1, H, W)
-    for _ in range(args.warmup):
-        om.forward_blu(anchor[:, :270])
+    image = formats.write_model_vect_c(model)
+    sample_frames = 4
+    anchor, _ = synth.make_frames(0xC0FFEE + 3, sample_frames, H, W)
+    om = oracle.OracleModel(image)
+    # CPU port: one frame per step, bounded
+    om.forward_blu(anchor[:1, :270])
+    cpu_steps = max(1, min(args.steps, 4))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        om.forward_blu(anchor)
-    dt = time.perf_counter() - t0
-    mpx = args.steps * H * W / dt / 1e6
+    for i in range(cpu_steps):
+        cpu_out = om.forward_blu(anchor[i % sample_frames:i % sample_frames + 1])
+    cpu_dt = time.perf_counter() - t0
+    cpu_mpx = cpu_steps * H * W / cpu_dt / 1e6
     cores = oracle.num_threads()
-    line = {"impl": "reference", "metric": "luma Mpixel/s (QVRCNN int8, 1080p)", "value": mpx, "unit": "Mpixel/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+    cpu_block = {"value": cpu_mpx, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                 "sample": "%d x one 1920x1080 frame, OpenMP C oracle (oracle/qvrcnn_oracle.c)" % cpu_steps}
+    kind, value, ms_per_step, note, matches = "port", cpu_mpx, cpu_dt / cpu_steps * 1e3, "CPU oracle port (no GPU or no witness binary)", None
+    if args.reference_kind != "cpu" and os.path.exists(REF_BIN) and _gpu_present():
+        with tempfile.TemporaryDirectory() as td:
+            mf, fi, fo = os.path.join(td, "m.data"), os.path.join(td, "in.luma"), os.path.join(td, "out.luma")
+            open(mf, "wb").write(image)
+            anchor.tofile(fi)
+            reps = args.warmup + args.steps
+            p = subprocess.run([REF_BIN, mf, str(H), str(W), str(sample_frames), fi, fo, str(reps)], capture_output=True, text=True, timeout=900)
+            times = [int(l.split(":")[1]) for l in p.stdout.splitlines() if l.startswith("time_us:")]
+            if p.returncode == 0 and len(times) == reps:
+                timed = times[args.warmup:]
+                tot = sum(timed) * 1e-6
+                value = len(timed) * sample_frames * H * W / tot / 1e6
+                ms_per_step = tot / len(timed) * 1e3
+                kind = "reference"
+                note = "unmodified reference sources (inference/*.cu) + cuDNN on GPU 0, one frame per forward_blu, " \
+                       "timer scope of inference/kernel.cu:89-101 (H2D + forward_blu + sync + D2H)"
+                rec = np.fromfile(fo, np.uint8).reshape(sample_frames, H, W)
+                matches = bool(np.array_equal(rec[:1], om.forward_blu(anchor[:1])))
+            else:
+                note = "witness binary failed (rc=%d): %s" % (p.returncode, (p.stderr or p.stdout)[-200:].replace("\n", " "))
+    line = {"impl": "reference", "metric": "luma Mpixel/s (QVRCNN int8, 1080p)", "value": value, "unit": "Mpixel/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "one 1920x1080 frame of the batch per step"},
-            "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-                             "sample": "%d x one 1920x1080 frame, OpenMP C oracle (oracle/qvrcnn_oracle.c)" % args.steps},
-            "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": {"workload": WORKLOAD, "sample": "%d frames of 1920x1080 from the batch per step" % sample_frames,
+                       "reference_kind": kind, "note": note},
+            "cpu_baseline": cpu_block,
+            "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if matches is not None:
+        line["reference_output_matches_oracle"] = matches
     print(json.dumps(line))
 
 
@@ -120,13 +165,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "fused", "layered"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-kind", default="auto", choices=["auto", "cpu"],
+                    help="--impl reference: auto = the real reference (cuDNN) when it can run, cpu = the CPU port only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps > 6:
-            args.steps = 6                      # bounded: ~3-4 s of CPU per 1080p frame
+        args.steps = max(1, min(args.steps, 20))
         run_reference(args, rank, world)
         return
 
