@@ -1,25 +1,36 @@
 // Fused QVRCNN forward for sm_100a: the whole network per column strip, activations resident in
-// shared memory, all five dense convolutions (and C1, via an in-smem im2col) as tcgen05.mma
-// kind::i8 implicit GEMMs with int32 accumulators in TMEM; HBM sees one luma byte in and one
-// reconstructed byte out per pixel.  Replaces, for one frame batch, the whole of
-// qvrcnn::forward_blu (inference/qvrcnn.cu:168-242): ppro, 6 x (cudnnConvolutionForward +
-// cudnnAddTensor), quantize_out_blu / concat_blu, applyRes_y.
+// shared memory, ALL six convolutions as tcgen05.mma kind::i8 implicit GEMMs with int32 accumulators
+// in TMEM; HBM sees one luma byte in and one reconstructed byte out per pixel.  Replaces, for one
+// frame batch, the whole of qvrcnn::forward_blu (inference/qvrcnn.cu:168-242): ppro, 6 x
+// (cudnnConvolutionForward + cudnnAddTensor), quantize_out_blu / concat_blu, applyRes_y.
 //
 // Geometry.  A CTA owns a work unit = (frame, column strip of WT=120 output pixels, row segment)
 // and rolls down the rows.  Every activation row lives in smem as [16-channel plane][pixel][16 B]
-// with a pixel pitch of PW=136: that is the canonical no-swizzle K-major UMMA operand layout
-// (8-pixel x 16-byte core matrices, SBO = 128 B, LBO = plane stride), so a convolution tap (r, s)
-// is nothing but a different start address in the A descriptor: row slot r, pixel offset s.
-// Buffer pixel p of a strip whose first output column is X0 maps to image column X0 - 8 + p.
+// with a pixel pitch of PW=136: the canonical no-swizzle K-major UMMA operand layout (8-pixel x
+// 16-byte core matrices, SBO = 128 B, LBO = plane stride), so a horizontal tap s is nothing but a
+// different start address in the A descriptor.  Buffer pixel p of a strip whose first output
+// column is X0 maps to image column X0 - 8 + p:
 //   input  p in [2,134)   a1: p = 4+m   a2: p = 6+m   a3: p = 7+m   out: p = 8+m  (m = MMA row)
 //
-// Pipeline.  9 warps: warps 0-7 are workers (TMEM->BLU->smem epilogues, im2col for C1, C4 + the
-// residual on CUDA cores, global I/O), warp 8 lane 0 issues every MMA.  Iteration i handles
-//   MMA side   : L1 for a1 row R1=y0-4+i, L2 for a2 row R1-4, L3 for a3 row R1-7  -> TMEM D*[i&1]
-//   worker side: epilogues of iteration i-1's accumulators (a1 row R1-1, a2 row R1-5, a3 row
-//                R1-8), im2col of input rows for a1 row R1+1, then C4 for output row R1-9.
-// The two sides meet at two mbarriers per iteration (work_done -> MMA may issue i+1,
-// mma_done -> workers may read D*[i&1] and overwrite the smem rows iteration i read).
+// Row scatter with accumulator rings.  An M=128 int8 MMA costs >= 44 cycles whatever N is (measured,
+// profiles/r1_probe_thr2.log), so per-tap MMAs with N = 16..48 waste the tensor pipe and, worse,
+// re-read every activation row from smem once per vertical tap.  Instead each activation row is
+// read once per horizontal shift and multiplied by the weights of ALL vertical taps at once:
+//   D[pixel, (out_row, k)] += A[in_row, pixel+s][c] * W[r = in_row - out_row + pad][s][c][k]
+// The accumulators of the output rows in flight form a ring in TMEM (slot = out_row mod ring
+// size); one MMA covers the whole ring, so N = 96 / 128 / 64 / 32.  The B operand for a ring of R
+// slots is stored as the block sequence [r_max .. r_0, Z] repeated (Z = zero block) and the
+// rotation that matches "slot = row mod R" is a start-address offset into it.  The slot of the
+// output row completed one step ago sits under the Z block (the MMA adds 0 to it) while the
+// workers drain it; the slot of the row that starts now is zeroed by one small MMA with a zero A.
+//
+// Pipeline.  9 warps: warps 0-7 are workers (TMEM -> requantise -> smem epilogues, im2col for C1,
+// residual + store), warp 8 issues every MMA (one elected lane).  Iteration i, R1 = y0-4+i:
+//   MMA side   : C1 for a1 row R1 (im2col operand); C2_2 scatter of a1 row R1-2; C2_1 scatter of a1
+//                row R1-3; C3_1 scatter of a2 row R1-6; C3_2 of a2 row R1-7; C4 scatter of a3 row R1-9
+//   worker side: drains what iteration i-1 completed: a1 row R1-1, a2 row R1-5, a3 row R1-8, output
+//                row R1-11 (+ residual, clamp, store); im2col for a1 row R1+1.
+// The two sides meet at two pairs of mbarriers per iteration.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -39,37 +50,45 @@ using namespace tc;
 constexpr int WT = 120;                    // output columns per strip
 constexpr int PW = 136;                    // pixel pitch of every activation row buffer
 constexpr int PLANE = PW * 16;             // bytes of one 16-channel plane of one row
-constexpr int PW16 = PW;                   // the same in 16-byte units
-constexpr int A1_SLOTS = 6, A2_SLOTS = 4, A3_SLOTS = 4, IN_SLOTS = 16, IN_PITCH = 144;
+constexpr int A_SLOTS = 3, IN_SLOTS = 32, IN_PITCH = 144;
 constexpr int A1_ROW = 4 * PLANE, A2_ROW = 3 * PLANE, A3_ROW = 3 * PLANE;
 constexpr int IM_BYTES = 2 * 128 * 16;     // one im2col A operand for C1: [2 K-planes][128 px][16 B]
+constexpr int ZERO_BYTES = 2 * 128 * 16;   // all-zero A operand (ring-slot initialisation)
 
-constexpr int W1_BYTES = 2 * 64 * 16;                  // [2][64][16]
-constexpr int W2_INNER = 2 * 48 * 16, W2_OUTER = 2 * 16 * 16;
-constexpr int W2_BYTES = 18 * W2_INNER + 32 * W2_OUTER;   // 44032
-constexpr int W3_BIG = 2 * 48 * 16, W3_SMALL = 2 * 16 * 16;
-constexpr int W3_BYTES = 2 * W3_BIG + 13 * W3_SMALL;      // 9728
-constexpr int BIAS_INTS = 64 + 48 + 48;
-
+// ---- B operands (weights) in smem: every block is [2 K-chunks][NR rows][16 B] ---------------------
+constexpr int NR22 = 11 * 16, NR21 = 7 * 32, NR31 = 7 * 16, NR32 = 32, NR4 = 7 * 8;
+constexpr int W1_BYTES = 2 * 64 * 16;
+constexpr int T22 = 2 * NR22 * 16, T21 = 2 * NR21 * 16, T31 = 2 * NR31 * 16, T32 = 2 * NR32 * 16, T4 = 2 * NR4 * 16;
 constexpr int OFF_W1 = 0;
-constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
-constexpr int OFF_W3 = OFF_W2 + W2_BYTES;
-constexpr int OFF_BIAS = OFF_W3 + W3_BYTES;
-constexpr int WIMG_BYTES = OFF_BIAS + BIAS_INTS * 4;        // what lives in global memory per model
+constexpr int OFF_W22 = OFF_W1 + W1_BYTES;      // 10 tiles (s, h)
+constexpr int OFF_W21 = OFF_W22 + 10 * T22;     //  6 tiles (s', h)
+constexpr int OFF_W31 = OFF_W21 + 6 * T21;      //  5 K-steps
+constexpr int OFF_W32 = OFF_W31 + 5 * T31;      //  2 K-steps
+constexpr int OFF_W4 = OFF_W32 + 2 * T32;       //  5 K-steps
+constexpr int OFF_BIAS = OFF_W4 + 5 * T4;
+constexpr int BIAS_INTS = 64 + 48 + 48;
+constexpr int WIMG_BYTES = OFF_BIAS + BIAS_INTS * 4;         // what lives in global memory per model
 constexpr int OFF_A1 = (WIMG_BYTES + 127) / 128 * 128;
-constexpr int OFF_A2 = OFF_A1 + A1_SLOTS * A1_ROW;
-constexpr int OFF_A3 = OFF_A2 + A2_SLOTS * A2_ROW;
-constexpr int OFF_IM = OFF_A3 + A3_SLOTS * A3_ROW;
-constexpr int OFF_IN = OFF_IM + 2 * IM_BYTES;
-constexpr int OFF_PART = OFF_IN + IN_SLOTS * IN_PITCH;     // C4 partial sums, 128 ints
-constexpr int OFF_CTRL = OFF_PART + 512;
+constexpr int OFF_A2 = OFF_A1 + A_SLOTS * A1_ROW;
+constexpr int OFF_A3 = OFF_A2 + A_SLOTS * A2_ROW;
+constexpr int OFF_IM = OFF_A3 + A_SLOTS * A3_ROW;
+constexpr int OFF_ZERO = OFF_IM + 2 * IM_BYTES;
+constexpr int OFF_IN = OFF_ZERO + ZERO_BYTES;
+constexpr int OFF_CTRL = OFF_IN + IN_SLOTS * IN_PITCH;
 constexpr int SMEM_BYTES = OFF_CTRL + 64;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
 constexpr int NWORKER = 256, NTHREADS = NWORKER + 32;
-constexpr int PIPE = 13;                   // pipeline depth in rows (first output row appears at i = 13)
+constexpr int PIPE = 15;                   // pipeline depth in rows: output row y0 appears at iteration 15
 
-// TMEM columns (int32 accumulators), double-buffered by iteration parity
-constexpr int TM_D1 = 0, TM_D2 = 128, TM_D3 = 224, TM_COLS = 512;
+// ---- TMEM columns (int32 accumulators) -------------------------------------------------------------
+constexpr int TM_D1 = 0;        // C1: 2 x 64, double-buffered by iteration parity
+constexpr int TM_R22 = 128;     // C2_2 ring: 6 slots x 16
+constexpr int TM_R21 = 224;     // C2_1 ring: 4 slots x 32
+constexpr int TM_R31 = 352;     // C3_1 ring: 4 slots x 16
+constexpr int TM_D32 = 416;     // C3_2: 2 x 32, double-buffered
+constexpr int TM_R4 = 480;      // C4 ring: 4 slots x 8 (column 0 of each slot is the residual accumulator)
+constexpr int TM_COLS = 512;
 
 // Per 16-column accumulator group: everything the requantiser needs.
 struct GroupQ {
@@ -85,7 +104,6 @@ struct FusedParams {
     int n_frames, H, W, nstrips, nseg, seg_rows, n_units;
     GroupQ q1, q22, q21, q31, q32;
     int c4_bias, c4_mul, c4_shift;
-    int c4_w[108];                     // [tap][plane][4 words], 4 channels per word
     long long *dbg;                    // optional per-block phase timers (QV_FUSED_PROFILE=1), else null
 };
 
@@ -120,23 +138,6 @@ __device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const int
         o[v] = __byte_perm(__byte_perm(q[0], q[1], 0x0073), __byte_perm(q[2], q[3], 0x0073), 0x5410);
     }
     *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-}
-
-// Partial C4 dot product of one pixel over (tap, plane) units [U0, U0+NU): 16 channels per unit.
-template <int U0, int NU>
-__device__ __forceinline__ int c4_partial(const uint8_t *px, const int (&slot3)[3], const FusedParams &P)
-{
-    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-#pragma unroll
-    for (int u = U0; u < U0 + NU; ++u) {
-        const int t = u / 3, pl = u % 3, r = t / 3, sft = t % 3;
-        const uint4 v = *reinterpret_cast<const uint4 *>(px + slot3[r] + pl * PLANE + sft * 16);
-        acc0 = __dp4a((int)v.x, P.c4_w[u * 4 + 0], acc0);
-        acc1 = __dp4a((int)v.y, P.c4_w[u * 4 + 1], acc1);
-        acc2 = __dp4a((int)v.z, P.c4_w[u * 4 + 2], acc2);
-        acc3 = __dp4a((int)v.w, P.c4_w[u * 4 + 3], acc3);
-    }
-    return (acc0 + acc1) + (acc2 + acc3);
 }
 
 template <bool FAST>
@@ -179,98 +180,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         // The whole warp runs the control flow (so that descriptors stay in uniform registers);
         // one elected lane issues the tcgen05 instructions.
         const bool leader = elect_one();
-        {
-            uint32_t ev_work = 0, ev_mma = 0;
-            long long t_wait = 0, t_issue = 0, tc0 = clock64();
-            constexpr uint32_t ID64 = idesc_i8(128, 64), ID48 = idesc_i8(128, 48), ID16 = idesc_i8(128, 16);
-            constexpr uint32_t HI_A = (128u >> 4) | (1u << 14);                 // SBO = 128 B, version 1
-            const uint32_t a_lo_plane = (uint32_t)PW16 << 16;                    // LBO = one plane
-            const uint32_t w1_lo = ((sbase + OFF_W1) >> 4) | ((64u * 16 >> 4) << 16);
-            const uint32_t w2_lo48 = ((sbase + OFF_W2) >> 4) | ((48u * 16 >> 4) << 16);
-            const uint32_t w2_lo16 = ((sbase + OFF_W2 + 18 * W2_INNER) >> 4) | ((16u * 16 >> 4) << 16);
-            const uint32_t w3_lo48 = ((sbase + OFF_W3) >> 4) | ((48u * 16 >> 4) << 16);
-            const uint32_t w3_lo16 = ((sbase + OFF_W3 + 2 * W3_BIG) >> 4) | ((16u * 16 >> 4) << 16);
-            auto desc = [](uint32_t lo) { return ((uint64_t)HI_A << 32) | lo; };
-            auto MMA = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-                if (leader) mma_i8_ss(d, a, b, idesc, acc);
-            };
-            for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-                const int seg = unit % P.nseg;
-                const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
-                const int niter = y1 - y0 + PIPE;
-                for (int i = 0; i < niter; ++i) {
-                    const int R1 = y0 - 4 + i;
-                    if (!mbar_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1)) { *s_fail = 1; }
-                    ++ev_work;
-                    fence_after_sync();
-                    { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
-                    const uint32_t par = i & 1;
-                    // ---- L1: a1 row R1 = im2col[par] x W1 -------------------------------------
-                    MMA(tm + TM_D1 + par * 64, desc((((sbase + OFF_IM + par * IM_BYTES) >> 4)) | ((128u * 16 >> 4) << 16)),
-                              desc(w1_lo), ID64, 0);
-                    // ---- L2: a2 row R2 = R1-4 from a1 rows R2-2..R2+2 ---------------------------
-                    {
-                        uint32_t row16[5];
+        uint32_t ev_work = 0, ev_mma = 0;
+        long long t_wait = 0, t_issue = 0, tc0 = clock64();
+        constexpr uint32_t HI = (128u >> 4) | (1u << 14);                     // SBO = 128 B, descriptor version 1
+        auto desc = [](uint32_t addr_bytes, uint32_t lbo_bytes) {
+            return ((uint64_t)HI << 32) | (uint64_t)(((addr_bytes >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16));
+        };
+        auto MMA = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+            if (leader) mma_i8_ss(d, a, b, idesc, acc);
+        };
+        const uint64_t zeroA = desc(sbase + OFF_ZERO, 128 * 16);
+        const uint64_t anyB16 = desc(sbase + OFF_W1, 64 * 16);
+        for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
+            const int seg = unit % P.nseg;
+            const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
+            const int niter = y1 - y0 + PIPE;
+            for (int i = 0; i < niter; ++i) {
+                const int R1 = y0 - 4 + i;
+                if (!mbar_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1)) { *s_fail = 1; }
+                ++ev_work;
+                fence_after_sync();
+                { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
+                const uint32_t par = i & 1;
+                // ---- C1: a1 row R1 = im2col[par] x W1 (N = 64) --------------------------------
+                MMA(tm + TM_D1 + par * 64, desc(sbase + OFF_IM + par * IM_BYTES, 128 * 16), desc(sbase + OFF_W1, 64 * 16),
+                    idesc_i8(128, 64), 0);
+                // ---- C2_2 (5x5, 64 -> 16): scatter a1 row Ra into the 6-slot ring, N = 96 ----------
+                {
+                    const int Ra = R1 - 2;
+                    const uint32_t arow = sbase + OFF_A1 + mod_pos(Ra, A_SLOTS) * A1_ROW;
+                    const uint32_t boff = mod_pos(8 - mod_pos(Ra, 6), 6) * 16 * 16;      // window start: 16 rows per block
+                    MMA(tm + TM_R22 + mod_pos(Ra + 2, 6) * 16, zeroA, anyB16, idesc_i8(128, 16), 0);     // row Ra+2 starts
 #pragma unroll
-                        for (int r = 0; r < 5; ++r)
-                            row16[r] = ((sbase + OFF_A1 + mod_pos(R1 - 6 + r, A1_SLOTS) * A1_ROW) >> 4) | a_lo_plane;
-                        const uint32_t d2 = tm + TM_D2 + par * 48;
-                        // inner 3x3 taps: N = 48 ([C2_2 | C2_1]); the first one initialises all 48 columns
+                    for (int s = 0; s < 5; ++s)
 #pragma unroll
-                        for (int t = 0; t < 9; ++t)
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int r = 1 + t / 3, s = 1 + t % 3;
-                                MMA(d2, desc(row16[r] + h * 2 * PW16 + 4 + s),
-                                          desc(w2_lo48 + ((t * 2 + h) * W2_INNER >> 4)), ID48, (t | h) != 0);
-                            }
-                        // outer ring of the 5x5: N = 16 (C2_2 only, columns 0..15)
-                        int oi = 0;
-#pragma unroll
-                        for (int t = 0; t < 25; ++t) {
-                            const int r = t / 5, s = t % 5;
-                            if (r >= 1 && r <= 3 && s >= 1 && s <= 3) continue;
-#pragma unroll
-                            for (int h = 0; h < 2; ++h)
-                                MMA(d2, desc(row16[r] + h * 2 * PW16 + 4 + s),
-                                          desc(w2_lo16 + ((oi * 2 + h) * W2_OUTER >> 4)), ID16, 1);
-                            ++oi;
-                        }
-                    }
-                    // ---- L3: a3 row R3 = R1-7 from a2 rows R3-1..R3+1 ---------------------------
-                    {
-                        uint32_t row16[3];
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-                            row16[r] = (sbase + OFF_A2 + mod_pos(R1 - 8 + r, A2_SLOTS) * A2_ROW) >> 4;
-                        const uint32_t d3 = tm + TM_D3 + par * 48;
-                        const uint32_t lbo_px = 1u << 16;                       // LBO = 16 B: next pixel, same plane
-                        // the two K-steps that contain the centre tap carry C3_2 as well: N = 48
-                        MMA(d3, desc((row16[1] + 6 + 1) | a_lo_plane), desc(w3_lo48), ID48, 0);
-                        MMA(d3, desc((row16[1] + 2 * PW16 + 6 + 0) | lbo_px), desc(w3_lo48 + (W3_BIG >> 4)), ID48, 1);
-                        int bi = 0;
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                            for (int k = 0; k < 5; ++k) {
-                                if (r == 1 && (k == 1 || k == 3)) continue;
-                                uint32_t a;
-                                if (k < 3) a = (row16[r] + 6 + k) | a_lo_plane;                  // (s=k : planes 0,1)
-                                else if (k == 3) a = (row16[r] + 2 * PW16 + 6 + 0) | lbo_px;     // (s0 plane2 | s1 plane2)
-                                else a = (row16[r] + 2 * PW16 + 6 + 2) | lbo_px;                 // (s2 plane2 | zero weights)
-                                MMA(d3, desc(a), desc(w3_lo16 + (bi * W3_SMALL >> 4)), ID16, 1);
-                                ++bi;
-                            }
-                        }
-                    }
-                    if (leader) mma_commit(&bar_mma[ev_mma & 1]);
-                    ++ev_mma;
-                    __syncwarp();
-                    { const long long t = clock64(); t_issue += t - tc0; tc0 = t; }
+                        for (int h = 0; h < 2; ++h)
+                            MMA(tm + TM_R22, desc(arow + h * 2 * PLANE + (4 + s) * 16, PLANE),
+                                desc(sbase + OFF_W22 + (s * 2 + h) * T22 + boff, NR22 * 16), idesc_i8(128, 96), 1);
                 }
+                // ---- C2_1 (3x3, 64 -> 32): scatter a1 row R1-3 into the 4-slot ring, N = 128 ---------
+                {
+                    const int Ra = R1 - 3;
+                    const uint32_t arow = sbase + OFF_A1 + mod_pos(Ra, A_SLOTS) * A1_ROW;
+                    const uint32_t boff = mod_pos(1 - mod_pos(Ra, 4), 4) * 32 * 16;
+                    MMA(tm + TM_R21 + mod_pos(Ra + 1, 4) * 32, zeroA, anyB16, idesc_i8(128, 32), 0);
+#pragma unroll
+                    for (int s = 0; s < 3; ++s)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            MMA(tm + TM_R21, desc(arow + h * 2 * PLANE + (5 + s) * 16, PLANE),
+                                desc(sbase + OFF_W21 + (s * 2 + h) * T21 + boff, NR21 * 16), idesc_i8(128, 128), 1);
+                }
+                // ---- C3_1 (3x3, 48 -> 16): scatter a2 row Rb into the 4-slot ring, N = 64.  K-steps pair
+                //      16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights)
+                {
+                    const int Rb = R1 - 6;
+                    const uint32_t arow = sbase + OFF_A2 + mod_pos(Rb, A_SLOTS) * A2_ROW;
+                    const uint32_t boff = mod_pos(1 - mod_pos(Rb, 4), 4) * 16 * 16;
+                    MMA(tm + TM_R31 + mod_pos(Rb + 1, 4) * 16, zeroA, anyB16, idesc_i8(128, 16), 0);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const uint64_t a = k < 3 ? desc(arow + (6 + k) * 16, PLANE)
+                                                 : desc(arow + 2 * PLANE + (k == 3 ? 6 : 8) * 16, 16);
+                        MMA(tm + TM_R31, a, desc(sbase + OFF_W31 + k * T31 + boff, NR31 * 16), idesc_i8(128, 64), 1);
+                    }
+                }
+                // ---- C3_2 (1x1, 48 -> 32) of a2 row R1-7, N = 32 ------------------------------------
+                {
+                    const uint32_t arow = sbase + OFF_A2 + mod_pos(R1 - 7, A_SLOTS) * A2_ROW;
+                    MMA(tm + TM_D32 + par * 32, desc(arow + 7 * 16, PLANE), desc(sbase + OFF_W32, NR32 * 16), idesc_i8(128, 32), 0);
+                    MMA(tm + TM_D32 + par * 32, desc(arow + 2 * PLANE + 7 * 16, 16), desc(sbase + OFF_W32 + T32, NR32 * 16),
+                        idesc_i8(128, 32), 1);
+                }
+                // ---- C4 (3x3, 48 -> 1): scatter a3 row Rc into the 4-slot ring of 8-column slots, N = 32 ---
+                {
+                    const int Rc = R1 - 9;
+                    const uint32_t arow = sbase + OFF_A3 + mod_pos(Rc, A_SLOTS) * A3_ROW;
+                    const uint32_t boff = mod_pos(1 - mod_pos(Rc, 4), 4) * 8 * 16;
+                    MMA(tm + TM_R4 + mod_pos(Rc + 1, 4) * 8, zeroA, anyB16, idesc_i8(128, 8), 0);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const uint64_t a = k < 3 ? desc(arow + (7 + k) * 16, PLANE)
+                                                 : desc(arow + 2 * PLANE + (k == 3 ? 7 : 9) * 16, 16);
+                        MMA(tm + TM_R4, a, desc(sbase + OFF_W4 + k * T4 + boff, NR4 * 16), idesc_i8(128, 32), 1);
+                    }
+                }
+                if (leader) mma_commit(&bar_mma[ev_mma & 1]);
+                ++ev_mma;
+                __syncwarp();
+                { const long long t = clock64(); t_issue += t - tc0; tc0 = t; }
             }
-            if (P.dbg && leader) { P.dbg[blockIdx.x * 16 + 0] = t_wait; P.dbg[blockIdx.x * 16 + 1] = t_issue; }
         }
+        if (P.dbg && leader) { P.dbg[blockIdx.x * 16 + 0] = t_wait; P.dbg[blockIdx.x * 16 + 1] = t_issue; }
     } else {
         // ================================= workers =========================================
         const int q = warp & 3, hh = warp >> 2;
@@ -334,40 +335,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     fence_after_sync();
                     lap(0);
                     const uint32_t par = (i - 1) & 1;
-                    // ---- epilogues: a1 row R1-1 (D1, 4 groups), a2 row R1-5 (D2: group 0 = C2_2 -> plane 2,
-                    //      groups 1,2 = C2_1 -> planes 0,1), a3 row R1-8 (D3: group 0 = C3_1, 1,2 = C3_2).
-                    //      Each warp half (hh) takes 5 of the 10 sixteen-column groups; all TMEM loads first.
-                    {
-                        const int row1 = R1 - 1, row2 = R1 - 5, row3 = R1 - 8;
-                        const bool v1 = row1 >= 0 && row1 < H && X0 - 4 + m >= 0 && X0 - 4 + m < W;
-                        const bool v2 = row2 >= 0 && row2 < H && X0 - 2 + m >= 0 && X0 - 2 + m < W;
-                        const bool v3 = row3 >= 0 && row3 < H && X0 - 1 + m >= 0 && X0 - 1 + m < W;
-                        uint8_t *dst1 = sm + OFF_A1 + mod_pos(row1, A1_SLOTS) * A1_ROW + (4 + m) * 16;
-                        uint8_t *dst2 = sm + OFF_A2 + mod_pos(row2, A2_SLOTS) * A2_ROW + (6 + m) * 16;
-                        uint8_t *dst3 = sm + OFF_A3 + mod_pos(row3, A3_SLOTS) * A3_ROW + (7 + m) * 16;
-                        const uint32_t d1 = tm_lane + TM_D1 + par * 64, d2 = tm_lane + TM_D2 + par * 48, d3 = tm_lane + TM_D3 + par * 48;
-                        uint32_t ra[16], rb[16], rc[16], rd[16], re[16];
-                        if (hh == 0) {
-                            tmem_ld_x16(d1 + 0, ra); tmem_ld_x16(d1 + 16, rb);
-                            tmem_ld_x16(d2 + 0, rc); tmem_ld_x16(d2 + 16, rd);
-                            tmem_ld_x16(d3 + 0, re);
-                            tmem_ld_wait();
-                            requant_store<FAST>(ra, s_bias + 0, P.q1, v1, dst1 + 0 * PLANE);
-                            requant_store<FAST>(rb, s_bias + 16, P.q1, v1, dst1 + 1 * PLANE);
-                            requant_store<FAST>(rc, s_bias + 64 + 0, P.q22, v2, dst2 + 2 * PLANE);
-                            requant_store<FAST>(rd, s_bias + 64 + 16, P.q21, v2, dst2 + 0 * PLANE);
-                            requant_store<FAST>(re, s_bias + 112 + 0, P.q31, v3, dst3 + 0 * PLANE);
-                        } else {
-                            tmem_ld_x16(d1 + 32, ra); tmem_ld_x16(d1 + 48, rb);
-                            tmem_ld_x16(d2 + 32, rc);
-                            tmem_ld_x16(d3 + 16, rd); tmem_ld_x16(d3 + 32, re);
-                            tmem_ld_wait();
-                            requant_store<FAST>(ra, s_bias + 32, P.q1, v1, dst1 + 2 * PLANE);
-                            requant_store<FAST>(rb, s_bias + 48, P.q1, v1, dst1 + 3 * PLANE);
-                            requant_store<FAST>(rc, s_bias + 64 + 32, P.q21, v2, dst2 + 1 * PLANE);
-                            requant_store<FAST>(rd, s_bias + 112 + 16, P.q32, v3, dst3 + 1 * PLANE);
-                            requant_store<FAST>(re, s_bias + 112 + 32, P.q32, v3, dst3 + 2 * PLANE);
+                    // ---- drain what iteration i-1 completed.  Ten 16-column groups, five per warp half:
+                    //      a1 row R1-1 : D1[par] groups 0..3                      -> a1 planes 0..3
+                    //      a2 row R1-5 : C2_2 ring slot (16) -> plane 2 ; C2_1 ring slot (32) -> planes 0,1
+                    //      a3 row R1-8 : C3_1 ring slot (16) -> plane 0 ; C3_2 D32[par] (32)   -> planes 1,2
+                    //      out row R1-11: C4 ring slot, column 0 (warp half 0)
+                    const int row1 = R1 - 1, row2 = R1 - 5, row3 = R1 - 8, row4 = R1 - 11;
+                    const bool v1 = row1 >= 0 && row1 < H && X0 - 4 + m >= 0 && X0 - 4 + m < W;
+                    const bool v2 = row2 >= 0 && row2 < H && X0 - 2 + m >= 0 && X0 - 2 + m < W;
+                    const bool v3 = row3 >= 0 && row3 < H && X0 - 1 + m >= 0 && X0 - 1 + m < W;
+                    uint8_t *dst1 = sm + OFF_A1 + mod_pos(row1, A_SLOTS) * A1_ROW + (4 + m) * 16;
+                    uint8_t *dst2 = sm + OFF_A2 + mod_pos(row2, A_SLOTS) * A2_ROW + (6 + m) * 16;
+                    uint8_t *dst3 = sm + OFF_A3 + mod_pos(row3, A_SLOTS) * A3_ROW + (7 + m) * 16;
+                    const uint32_t d1 = tm_lane + TM_D1 + par * 64;
+                    const uint32_t d22 = tm_lane + TM_R22 + mod_pos(row2, 6) * 16, d21 = tm_lane + TM_R21 + mod_pos(row2, 4) * 32;
+                    const uint32_t d31 = tm_lane + TM_R31 + mod_pos(row3, 4) * 16, d32 = tm_lane + TM_D32 + par * 32;
+                    uint32_t ra[16], rb[16], rc[16], rd[16], re[16];
+                    if (hh == 0) {
+                        tmem_ld_x16(d1 + 0, ra); tmem_ld_x16(d1 + 16, rb);
+                        tmem_ld_x16(d22, rc); tmem_ld_x16(d21, rd);
+                        tmem_ld_x16(d31, re);
+                        const uint32_t u4raw = tmem_ld_x1(tm_lane + TM_R4 + mod_pos(row4, 4) * 8);
+                        tmem_ld_wait();
+                        requant_store<FAST>(ra, s_bias + 0, P.q1, v1, dst1 + 0 * PLANE);
+                        requant_store<FAST>(rb, s_bias + 16, P.q1, v1, dst1 + 1 * PLANE);
+                        requant_store<FAST>(rc, s_bias + 64 + 0, P.q22, v2, dst2 + 2 * PLANE);
+                        requant_store<FAST>(rd, s_bias + 64 + 16, P.q21, v2, dst2 + 0 * PLANE);
+                        requant_store<FAST>(re, s_bias + 112 + 0, P.q31, v3, dst3 + 0 * PLANE);
+                        // applyRes_y (cnn.cu:507-523) on the finished C4 accumulator
+                        if (row4 >= y0 && row4 < y1 && m < WT && X0 + m < W) {
+                            const int x = sm[OFF_IN + mod_pos(row4, IN_SLOTS) * IN_PITCH + 8 + m];
+                            outf[(size_t)row4 * W + X0 + m] = (uint8_t)residual_apply((int)u4raw + P.c4_bias, x, P.c4_mul, P.c4_shift);
                         }
+                    } else {
+                        tmem_ld_x16(d1 + 32, ra); tmem_ld_x16(d1 + 48, rb);
+                        tmem_ld_x16(d21 + 16, rc);
+                        tmem_ld_x16(d32 + 0, rd); tmem_ld_x16(d32 + 16, re);
+                        tmem_ld_wait();
+                        requant_store<FAST>(ra, s_bias + 32, P.q1, v1, dst1 + 2 * PLANE);
+                        requant_store<FAST>(rb, s_bias + 48, P.q1, v1, dst1 + 3 * PLANE);
+                        requant_store<FAST>(rc, s_bias + 64 + 32, P.q21, v2, dst2 + 1 * PLANE);
+                        requant_store<FAST>(rd, s_bias + 112 + 16, P.q32, v3, dst3 + 1 * PLANE);
+                        requant_store<FAST>(re, s_bias + 112 + 32, P.q32, v3, dst3 + 2 * PLANE);
                     }
                 }
                 lap(1);
@@ -381,27 +390,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 }
                 lap(2);
                 store_in(R1 + 4, in_next);
-                worker_bar();                                     // a3 row + input ring visible to every worker
+                worker_bar();                                     // input ring visible to the im2col warps of the next iteration
                 lap(3);
-                // ---- C4 (48 -> 1, 3x3) + applyRes_y for output row R1-9 (cnn.cu:507-523).  The 27 (tap, plane)
-                //      units of a pixel are split 13 / 14 between the two warp halves; partial sums meet in smem.
-                const int R4 = R1 - 9;
-                if (R4 >= y0 && R4 < y1) {
-                    const uint8_t *px = sm + OFF_A3 + (7 + m) * 16;
-                    int slot3[3];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) slot3[r] = mod_pos(R4 - 1 + r, A3_SLOTS) * A3_ROW;
-                    const int part = hh == 0 ? c4_partial<0, 13>(px, slot3, P) : c4_partial<13, 14>(px, slot3, P);
-                    int *s_part = reinterpret_cast<int *>(sm + OFF_PART);
-                    if (hh == 1) s_part[m] = part;
-                    worker_bar();
-                    if (hh == 0 && m < WT && X0 + m < W) {
-                        const int x = sm[OFF_IN + mod_pos(R4, IN_SLOTS) * IN_PITCH + 8 + m];
-                        outf[(size_t)R4 * W + X0 + m] =
-                            (uint8_t)residual_apply(part + s_part[m] + P.c4_bias, x, P.c4_mul, P.c4_shift);
-                    }
-                }
-                lap(4);
             }
             // drain: the MMAs of the last iteration still read smem / write TMEM
             if (!mbar_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1)) { *s_fail = 1; }
@@ -429,12 +419,13 @@ struct FusedModel {
     int sm_count = 148;
 };
 
-static void put_chunk(uint8_t *blk, int N, int kchunk, int n, const int8_t *src16) { memcpy(blk + ((size_t)kchunk * N + n) * 16, src16, 16); }
+// Writes 16 K-bytes of row n, K-chunk j, of a B block laid out [2][NR][16].
+static void put_chunk(uint8_t *blk, int NR, int j, int n, const int8_t *src16) { memcpy(blk + ((size_t)j * NR + n) * 16, src16, 16); }
 
 FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
 {
     std::vector<uint8_t> img(WIMG_BYTES, 0);
-    auto W = [&](int l, int k, int c, int r, int s) -> int8_t {
+    auto Wt = [&](int l, int k, int c, int r, int s) -> int8_t {
         const LayerShape &sh = kLayers[l];
         return m.L[l].w[(((size_t)k * sh.cin + c) * sh.k + r) * sh.k + s];
     };
@@ -442,69 +433,69 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     for (int n = 0; n < 64; ++n) {
         int8_t k32[32] = {0};
         for (int r = 0; r < 5; ++r) {
-            for (int s = 0; s < 4; ++s) k32[4 * r + s] = W(QV_C1, n, 0, r, s);
-            k32[20 + r] = W(QV_C1, n, 0, r, 4);
+            for (int s = 0; s < 4; ++s) k32[4 * r + s] = Wt(QV_C1, n, 0, r, s);
+            k32[20 + r] = Wt(QV_C1, n, 0, r, 4);
         }
         put_chunk(img.data() + OFF_W1, 64, 0, n, k32);
         put_chunk(img.data() + OFF_W1, 64, 1, n, k32 + 16);
     }
-    // ---- W2: 18 inner blocks (N=48: rows 0..15 = C2_2, 16..47 = C2_1) then 32 outer blocks (N=16: C2_2)
-    {
-        int oi = 0;
-        for (int t = 0; t < 25; ++t) {
-            const int r = t / 5, s = t % 5;
-            const bool inner = r >= 1 && r <= 3 && s >= 1 && s <= 3;
-            for (int h = 0; h < 2; ++h) {
-                uint8_t *blk;
-                int N;
-                if (inner) { const int ti = (r - 1) * 3 + (s - 1); blk = img.data() + OFF_W2 + (ti * 2 + h) * W2_INNER; N = 48; }
-                else { blk = img.data() + OFF_W2 + 18 * W2_INNER + (oi * 2 + h) * W2_OUTER; N = 16; }
-                for (int j = 0; j < 2; ++j) {
-                    int8_t c16[16];
-                    for (int n = 0; n < 16; ++n) {
-                        for (int b = 0; b < 16; ++b) c16[b] = W(QV_C2_2, n, 32 * h + 16 * j + b, r, s);
-                        put_chunk(blk, N, j, n, c16);
-                    }
-                    if (inner)
-                        for (int n = 0; n < 32; ++n) {
-                            for (int b = 0; b < 16; ++b) c16[b] = W(QV_C2_1, n, 32 * h + 16 * j + b, r - 1, s - 1);
-                            put_chunk(blk, N, j, 16 + n, c16);
+    // Ring block sequences: vertical tap r per block (-1 = zero block); a window of R consecutive blocks,
+    // starting at the offset the kernel computes from (row mod R), lines the taps up with the ring slots.
+    const int S22[11] = {4, 3, 2, 1, 0, -1, 4, 3, 2, 1, 0};
+    const int S3[7] = {2, 1, 0, -1, 2, 1, 0};
+    int8_t c16[16];
+    // ---- W22: tile (s, h): rows blk*16 + ch ; channels 32h + 16j + b ------------------------------
+    for (int s = 0; s < 5; ++s)
+        for (int h = 0; h < 2; ++h) {
+            uint8_t *blk = img.data() + OFF_W22 + (s * 2 + h) * T22;
+            for (int bi = 0; bi < 11; ++bi)
+                if (S22[bi] >= 0)
+                    for (int j = 0; j < 2; ++j)
+                        for (int ch = 0; ch < 16; ++ch) {
+                            for (int b = 0; b < 16; ++b) c16[b] = Wt(QV_C2_2, ch, 32 * h + 16 * j + b, S22[bi], s);
+                            put_chunk(blk, NR22, j, bi * 16 + ch, c16);
                         }
-                }
-            }
-            if (!inner) ++oi;
         }
-    }
-    // ---- W3: K-steps are pairs of (tap, 16-channel plane) units of a2 ----------------------------
-    {
-        // unit (r, s, pl) -> 16 weights per output row; C3_1 rows 0..15, C3_2 rows 16..47 (centre tap only)
-        auto fill = [&](uint8_t *blk, int N, int j, int r, int s, int pl) {
-            int8_t c16[16];
-            for (int n = 0; n < 16; ++n) {
-                for (int b = 0; b < 16; ++b) c16[b] = W(QV_C3_1, n, 16 * pl + b, r, s);
-                put_chunk(blk, N, j, n, c16);
-            }
-            if (N == 48 && r == 1 && s == 1)
-                for (int n = 0; n < 32; ++n) {
-                    for (int b = 0; b < 16; ++b) c16[b] = W(QV_C3_2, n, 16 * pl + b, 0, 0);
-                    put_chunk(blk, N, j, 16 + n, c16);
+    // ---- W21: tile (s', h): rows blk*32 + ch --------------------------------------------------------
+    for (int s = 0; s < 3; ++s)
+        for (int h = 0; h < 2; ++h) {
+            uint8_t *blk = img.data() + OFF_W21 + (s * 2 + h) * T21;
+            for (int bi = 0; bi < 7; ++bi)
+                if (S3[bi] >= 0)
+                    for (int j = 0; j < 2; ++j)
+                        for (int ch = 0; ch < 32; ++ch) {
+                            for (int b = 0; b < 16; ++b) c16[b] = Wt(QV_C2_1, ch, 32 * h + 16 * j + b, S3[bi], s);
+                            put_chunk(blk, NR21, j, bi * 32 + ch, c16);
+                        }
+        }
+    // ---- K-step -> (s, plane) units of a 48-channel activation row -----------------------------------
+    //   k = 0,1,2: (s=k, plane 0) | (s=k, plane 1) ;  k = 3: (s=0, plane 2) | (s=1, plane 2) ;  k = 4: (s=2, plane 2) | zero
+    auto unit = [](int k, int j, int &s, int &pl) -> bool {
+        if (k < 3) { s = k; pl = j; return true; }
+        if (k == 3) { s = j; pl = 2; return true; }
+        s = 2; pl = 2;
+        return j == 0;
+    };
+    // ---- W31 (rows blk*16 + ch) and W4 (rows blk*8 + 0; rows blk*8 + 1..7 stay zero) ------------------
+    for (int k = 0; k < 5; ++k)
+        for (int bi = 0; bi < 7; ++bi)
+            if (S3[bi] >= 0)
+                for (int j = 0; j < 2; ++j) {
+                    int s, pl;
+                    if (!unit(k, j, s, pl)) continue;
+                    for (int ch = 0; ch < 16; ++ch) {
+                        for (int b = 0; b < 16; ++b) c16[b] = Wt(QV_C3_1, ch, 16 * pl + b, S3[bi], s);
+                        put_chunk(img.data() + OFF_W31 + k * T31, NR31, j, bi * 16 + ch, c16);
+                    }
+                    for (int b = 0; b < 16; ++b) c16[b] = Wt(QV_C4, 0, 16 * pl + b, S3[bi], s);
+                    put_chunk(img.data() + OFF_W4 + k * T4, NR4, j, bi * 8, c16);
                 }
-        };
-        uint8_t *big = img.data() + OFF_W3;
-        fill(big, 48, 0, 1, 1, 0); fill(big, 48, 1, 1, 1, 1);                       // (r1,s1: planes 0,1)
-        fill(big + W3_BIG, 48, 0, 1, 0, 2); fill(big + W3_BIG, 48, 1, 1, 1, 2);     // (r1,s0 plane 2 | r1,s1 plane 2)
-        uint8_t *small = img.data() + OFF_W3 + 2 * W3_BIG;
-        int bi = 0;
-        for (int r = 0; r < 3; ++r)
-            for (int k = 0; k < 5; ++k) {
-                if (r == 1 && (k == 1 || k == 3)) continue;
-                uint8_t *blk = small + bi * W3_SMALL;
-                if (k < 3) { fill(blk, 16, 0, r, k, 0); fill(blk, 16, 1, r, k, 1); }
-                else if (k == 3) { fill(blk, 16, 0, r, 0, 2); fill(blk, 16, 1, r, 1, 2); }
-                else { fill(blk, 16, 0, r, 2, 2); /* second half stays zero */ }
-                ++bi;
-            }
-    }
+    // ---- W32 (1x1): K-step 0 = planes 0,1 ; K-step 1 = plane 2 | zero --------------------------------
+    for (int ch = 0; ch < 32; ++ch)
+        for (int pl = 0; pl < 3; ++pl) {
+            for (int b = 0; b < 16; ++b) c16[b] = Wt(QV_C3_2, ch, 16 * pl + b, 0, 0);
+            put_chunk(img.data() + OFF_W32 + (pl / 2) * T32, NR32, pl % 2, ch, c16);
+        }
     // ---- requantiser constants ---------------------------------------------------------------------
     FusedModel *fm = new FusedModel();
     auto mkq = [&](int l, GroupQ &g) -> bool {
@@ -526,16 +517,9 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
         for (int k = 0; k < kLayers[l].cout; ++k) bias[dst0 + k] = m.L[l].b[k] + (fast ? g.rbias : 0);
     };
     addb(QV_C1, 0, P.q1);
-    addb(QV_C2_2, 64, P.q22); addb(QV_C2_1, 64 + 16, P.q21);       // D2 order: [C2_2 | C2_1]
-    addb(QV_C3_1, 112, P.q31); addb(QV_C3_2, 112 + 16, P.q32);     // D3 order: [C3_1 | C3_2]
+    addb(QV_C2_2, 64, P.q22); addb(QV_C2_1, 64 + 16, P.q21);
+    addb(QV_C3_1, 112, P.q31); addb(QV_C3_2, 112 + 16, P.q32);
     P.c4_bias = m.L[QV_C4].b[0]; P.c4_mul = m.L[QV_C4].mul; P.c4_shift = m.L[QV_C4].shift;
-    for (int t = 0; t < 9; ++t)
-        for (int pl = 0; pl < 3; ++pl)
-            for (int j = 0; j < 4; ++j) {
-                unsigned v = 0;
-                for (int b = 0; b < 4; ++b) v |= (unsigned)(uint8_t)W(QV_C4, 0, 16 * pl + 4 * j + b, t / 3, t % 3) << (8 * b);
-                P.c4_w[(t * 3 + pl) * 4 + j] = (int)v;
-            }
     cudaError_t e = cudaMalloc(&fm->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fm->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -600,10 +584,10 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
         for (int b = 0; b < grid; ++b) for (int k = 0; k < 14; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
         const double iters = (double)P.n_units / grid * (P.seg_rows + PIPE);
         fprintf(stderr, "[qv fused profile] units=%d grid=%d iters/block~%.0f | cycles per iteration: MMA warp wait=%.0f issue=%.0f | "
-                "worker w0 (C4 side): wait_mma=%.0f epi=%.0f im2col+arrive=%.0f bar=%.0f c4=%.0f drain=%.0f | "
-                "worker w4 (im2col side): wait_mma=%.0f epi=%.0f im2col+arrive=%.0f bar=%.0f c4=%.0f drain=%.0f\n",
-                P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[4] / iters, a[5] / iters, a[6] / iters,
-                a[7] / iters, a[8] / iters, a[9] / iters, a[10] / iters, a[11] / iters, a[12] / iters, a[13] / iters);
+                "worker w0: wait_mma=%.0f drain+epi=%.0f im2col+arrive=%.0f bar=%.0f | "
+                "worker w4: wait_mma=%.0f drain+epi=%.0f im2col+arrive=%.0f bar=%.0f\n",
+                P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[4] / iters, a[5] / iters,
+                a[8] / iters, a[9] / iters, a[10] / iters, a[11] / iters);
     }
     return e;
 }
