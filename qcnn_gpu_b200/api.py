@@ -17,7 +17,7 @@ from typing import Optional
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libqvrcnn_b200.so")
+LIB_PATH = os.environ.get("QVRCNN_B200_LIB", os.path.join(_PKG, "libqvrcnn_b200.so"))   # override: A/B builds only
 
 IMPL_AUTO, IMPL_LAYERED, IMPL_FUSED = 0, 1, 2
 

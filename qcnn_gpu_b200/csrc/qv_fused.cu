@@ -105,22 +105,38 @@ struct FusedParams {
     GroupQ q1, q22, q21, q31, q32;
     int c4_bias, c4_mul, c4_shift;
     long long *dbg;                    // optional per-block phase timers (QV_FUSED_PROFILE=1), else null
+    int dbg_flags;                     // tuning experiments only (QV_FUSED_EXPERIMENT): 1 = issue no MMAs, 2 = workers skip the drains
+    int bias[BIAS_INTS];               // per accumulator column: layer bias (+ rounding bias on the FAST path)
 };
 
 __device__ __forceinline__ int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
+// Ring indices without divisions: c3 / c6 track R1 mod 3 / mod 6 incrementally; (c - k) mod n for a
+// compile-time k is one compare-and-add.  Powers of two use masks on R1 + 4096 (R1 may be negative).
+__device__ __forceinline__ int wrap_sub(int c, int k, int n) { const int v = c - (k % n); return v < 0 ? v + n : v; }
+__device__ __forceinline__ int wrap_inc(int c, int n) { return c + 1 == n ? 0 : c + 1; }
+
+// One lane polls the mbarrier (every try_wait is a shared-memory access that competes with the tensor
+// core's operand fetches: 256 pollers measurably slow the MMAs down), the rest of the warp parks at
+// __syncwarp, which also carries the acquired memory ordering to them.
+__device__ __forceinline__ void warp_wait(uint64_t *bar, uint32_t parity, int lane, int *fail)
+{
+    if (lane == 0 && !tc::mbar_wait(bar, parity)) *fail = 1;
+    __syncwarp();
+}
+
 // ---- requantise 16 accumulator columns of this thread's pixel and store them as one 16-byte
 // ---- channel group of an activation row (mat.cu:262-303 folded into the TMEM epilogue)
-template <bool FAST>
-__device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const int *bias16, const GroupQ &g, bool valid,
+template <bool FAST, int BOFF>
+__device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const FusedParams &P, const GroupQ &g, bool valid,
                                               uint8_t *dst)
 {
     uint32_t o[4];
     const unsigned Mz = valid ? g.M : 0u;           // FAST: an out-of-image pixel multiplies by 0
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-        const int4 b = reinterpret_cast<const int4 *>(bias16)[v];
-        const int bb[4] = {b.x, b.y, b.z, b.w};
+        // biases sit in the kernel-parameter constant bank at compile-time offsets: no smem traffic
+        const int bb[4] = {P.bias[BOFF + 4 * v], P.bias[BOFF + 4 * v + 1], P.bias[BOFF + 4 * v + 2], P.bias[BOFF + 4 * v + 3]};
         uint32_t q[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -186,8 +202,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         auto desc = [](uint32_t addr_bytes, uint32_t lbo_bytes) {
             return ((uint64_t)HI << 32) | (uint64_t)(((addr_bytes >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16));
         };
+        const bool issue = leader && !(P.dbg_flags & 1);
         auto MMA = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-            if (leader) mma_i8_ss(d, a, b, idesc, acc);
+            if (issue) mma_i8_ss(d, a, b, idesc, acc);
         };
         const uint64_t zeroA = desc(sbase + OFF_ZERO, 128 * 16);
         const uint64_t anyB16 = desc(sbase + OFF_W1, 64 * 16);
@@ -195,9 +212,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             const int seg = unit % P.nseg;
             const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
-            for (int i = 0; i < niter; ++i) {
-                const int R1 = y0 - 4 + i;
-                if (!mbar_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1)) { *s_fail = 1; }
+            int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
+            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
+                const int R1 = y0 - 4 + i, R1p = R1 + 4096;
+                warp_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1, lane, s_fail);
                 ++ev_work;
                 fence_after_sync();
                 { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
@@ -207,10 +225,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     idesc_i8(128, 64), 0);
                 // ---- C2_2 (5x5, 64 -> 16): scatter a1 row Ra into the 6-slot ring, N = 96 ----------
                 {
-                    const int Ra = R1 - 2;
-                    const uint32_t arow = sbase + OFF_A1 + mod_pos(Ra, A_SLOTS) * A1_ROW;
-                    const uint32_t boff = mod_pos(8 - mod_pos(Ra, 6), 6) * 16 * 16;      // window start: 16 rows per block
-                    MMA(tm + TM_R22 + mod_pos(Ra + 2, 6) * 16, zeroA, anyB16, idesc_i8(128, 16), 0);     // row Ra+2 starts
+                    const uint32_t arow = sbase + OFF_A1 + wrap_sub(c3, 2, 3) * A1_ROW;          // a1 row Ra = R1-2
+                    const int qa = wrap_sub(c6, 2, 6);                                           // Ra mod 6
+                    const uint32_t boff = (qa <= 2 ? 2 - qa : 8 - qa) * 16 * 16;                 // window start (8 - qa) mod 6, 16 rows per block
+                    MMA(tm + TM_R22 + c6 * 16, zeroA, anyB16, idesc_i8(128, 16), 0);             // row Ra+2 = R1 starts
 #pragma unroll
                     for (int s = 0; s < 5; ++s)
 #pragma unroll
@@ -220,10 +238,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 }
                 // ---- C2_1 (3x3, 64 -> 32): scatter a1 row R1-3 into the 4-slot ring, N = 128 ---------
                 {
-                    const int Ra = R1 - 3;
-                    const uint32_t arow = sbase + OFF_A1 + mod_pos(Ra, A_SLOTS) * A1_ROW;
-                    const uint32_t boff = mod_pos(1 - mod_pos(Ra, 4), 4) * 32 * 16;
-                    MMA(tm + TM_R21 + mod_pos(Ra + 1, 4) * 32, zeroA, anyB16, idesc_i8(128, 32), 0);
+                    const uint32_t arow = sbase + OFF_A1 + c3 * A1_ROW;                          // a1 row Ra = R1-3 (== R1 mod 3)
+                    const uint32_t boff = ((1 - (R1p - 3)) & 3) * 32 * 16;                       // (1 - Ra mod 4) mod 4
+                    MMA(tm + TM_R21 + ((R1p - 2) & 3) * 32, zeroA, anyB16, idesc_i8(128, 32), 0);  // row Ra+1 starts
 #pragma unroll
                     for (int s = 0; s < 3; ++s)
 #pragma unroll
@@ -234,10 +251,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 // ---- C3_1 (3x3, 48 -> 16): scatter a2 row Rb into the 4-slot ring, N = 64.  K-steps pair
                 //      16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights)
                 {
-                    const int Rb = R1 - 6;
-                    const uint32_t arow = sbase + OFF_A2 + mod_pos(Rb, A_SLOTS) * A2_ROW;
-                    const uint32_t boff = mod_pos(1 - mod_pos(Rb, 4), 4) * 16 * 16;
-                    MMA(tm + TM_R31 + mod_pos(Rb + 1, 4) * 16, zeroA, anyB16, idesc_i8(128, 16), 0);
+                    const uint32_t arow = sbase + OFF_A2 + c3 * A2_ROW;                          // a2 row Rb = R1-6
+                    const uint32_t boff = ((1 - (R1p - 6)) & 3) * 16 * 16;
+                    MMA(tm + TM_R31 + ((R1p - 5) & 3) * 16, zeroA, anyB16, idesc_i8(128, 16), 0);
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
                         const uint64_t a = k < 3 ? desc(arow + (6 + k) * 16, PLANE)
@@ -247,17 +263,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 }
                 // ---- C3_2 (1x1, 48 -> 32) of a2 row R1-7, N = 32 ------------------------------------
                 {
-                    const uint32_t arow = sbase + OFF_A2 + mod_pos(R1 - 7, A_SLOTS) * A2_ROW;
+                    const uint32_t arow = sbase + OFF_A2 + wrap_sub(c3, 7, 3) * A2_ROW;
                     MMA(tm + TM_D32 + par * 32, desc(arow + 7 * 16, PLANE), desc(sbase + OFF_W32, NR32 * 16), idesc_i8(128, 32), 0);
                     MMA(tm + TM_D32 + par * 32, desc(arow + 2 * PLANE + 7 * 16, 16), desc(sbase + OFF_W32 + T32, NR32 * 16),
                         idesc_i8(128, 32), 1);
                 }
                 // ---- C4 (3x3, 48 -> 1): scatter a3 row Rc into the 4-slot ring of 8-column slots, N = 32 ---
                 {
-                    const int Rc = R1 - 9;
-                    const uint32_t arow = sbase + OFF_A3 + mod_pos(Rc, A_SLOTS) * A3_ROW;
-                    const uint32_t boff = mod_pos(1 - mod_pos(Rc, 4), 4) * 8 * 16;
-                    MMA(tm + TM_R4 + mod_pos(Rc + 1, 4) * 8, zeroA, anyB16, idesc_i8(128, 8), 0);
+                    const uint32_t arow = sbase + OFF_A3 + c3 * A3_ROW;                          // a3 row Rc = R1-9
+                    const uint32_t boff = ((1 - (R1p - 9)) & 3) * 8 * 16;
+                    MMA(tm + TM_R4 + ((R1p - 8) & 3) * 8, zeroA, anyB16, idesc_i8(128, 8), 0);
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
                         const uint64_t a = k < 3 ? desc(arow + (7 + k) * 16, PLANE)
@@ -277,7 +292,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         const int q = warp & 3, hh = warp >> 2;
         const int m = q * 32 + lane;                              // this thread's MMA row / pixel
         const uint32_t tm_lane = tm + ((uint32_t)(q * 32) << 16);
-        const int *s_bias = reinterpret_cast<const int *>(sm + OFF_BIAS);
         uint32_t ev_work = 0, ev_mma = 0;
         long long tw[6] = {0, 0, 0, 0, 0, 0}, tc0 = clock64();
         auto lap = [&](int k) { const long long t = clock64(); tw[k] += t - tc0; tc0 = t; };
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 return (in_col_ok && row >= 0 && row < H) ? (unsigned)inf[(size_t)row * W + col_in] : 128u;
             };
             auto store_in = [&](int row, unsigned v) {
-                if (tid < PW) sm[OFF_IN + mod_pos(row, IN_SLOTS) * IN_PITCH + tid] = (uint8_t)v;
+                if (tid < PW) sm[OFF_IN + ((row + 4096) & (IN_SLOTS - 1)) * IN_PITCH + tid] = (uint8_t)v;
             };
             // im2col of input rows R-2..R+2 for a1 row R (threads of warps 4-7: pixel m)
             auto im2col = [&](int R, int buf) {
@@ -303,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 const int p = m + 2, o8 = (p & 3) * 8;
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
-                    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm + OFF_IN + mod_pos(R - 2 + r, IN_SLOTS) * IN_PITCH) + (p >> 2);
+                    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm + OFF_IN + ((R + 4094 + r) & (IN_SLOTS - 1)) * IN_PITCH) + (p >> 2);
                     const uint32_t w0 = rowp[0], w1 = rowp[1];
                     A[r] = __funnelshift_r(w0, w1, o8);           // bytes p..p+3   (taps s = 0..3)
                     const uint32_t b = (w1 >> o8) & 0xffu;        // byte  p+4      (tap  s = 4)
@@ -326,11 +340,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
                 ++ev_work;
             }
-            for (int i = 0; i < niter; ++i) {
-                const int R1 = y0 - 4 + i;
+            int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
+            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
+                const int R1 = y0 - 4 + i, R1p = R1 + 4096;
                 const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
-                if (i >= 1) {
-                    if (!mbar_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1)) { *s_fail = 1; }
+                if (i >= 1 && (P.dbg_flags & 2)) {
+                    warp_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1, lane, s_fail);
+                    ++ev_mma;
+                    fence_after_sync();
+                    lap(0);
+                } else if (i >= 1) {
+                    warp_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1, lane, s_fail);
                     ++ev_mma;
                     fence_after_sync();
                     lap(0);
@@ -344,27 +364,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     const bool v1 = row1 >= 0 && row1 < H && X0 - 4 + m >= 0 && X0 - 4 + m < W;
                     const bool v2 = row2 >= 0 && row2 < H && X0 - 2 + m >= 0 && X0 - 2 + m < W;
                     const bool v3 = row3 >= 0 && row3 < H && X0 - 1 + m >= 0 && X0 - 1 + m < W;
-                    uint8_t *dst1 = sm + OFF_A1 + mod_pos(row1, A_SLOTS) * A1_ROW + (4 + m) * 16;
-                    uint8_t *dst2 = sm + OFF_A2 + mod_pos(row2, A_SLOTS) * A2_ROW + (6 + m) * 16;
-                    uint8_t *dst3 = sm + OFF_A3 + mod_pos(row3, A_SLOTS) * A3_ROW + (7 + m) * 16;
+                    uint8_t *dst1 = sm + OFF_A1 + wrap_sub(c3, 1, 3) * A1_ROW + (4 + m) * 16;
+                    uint8_t *dst2 = sm + OFF_A2 + wrap_sub(c3, 5, 3) * A2_ROW + (6 + m) * 16;
+                    uint8_t *dst3 = sm + OFF_A3 + wrap_sub(c3, 8, 3) * A3_ROW + (7 + m) * 16;
                     const uint32_t d1 = tm_lane + TM_D1 + par * 64;
-                    const uint32_t d22 = tm_lane + TM_R22 + mod_pos(row2, 6) * 16, d21 = tm_lane + TM_R21 + mod_pos(row2, 4) * 32;
-                    const uint32_t d31 = tm_lane + TM_R31 + mod_pos(row3, 4) * 16, d32 = tm_lane + TM_D32 + par * 32;
+                    const uint32_t d22 = tm_lane + TM_R22 + wrap_sub(c6, 5, 6) * 16, d21 = tm_lane + TM_R21 + ((R1p - 5) & 3) * 32;
+                    const uint32_t d31 = tm_lane + TM_R31 + ((R1p - 8) & 3) * 16, d32 = tm_lane + TM_D32 + par * 32;
                     uint32_t ra[16], rb[16], rc[16], rd[16], re[16];
                     if (hh == 0) {
                         tmem_ld_x16(d1 + 0, ra); tmem_ld_x16(d1 + 16, rb);
                         tmem_ld_x16(d22, rc); tmem_ld_x16(d21, rd);
                         tmem_ld_x16(d31, re);
-                        const uint32_t u4raw = tmem_ld_x1(tm_lane + TM_R4 + mod_pos(row4, 4) * 8);
+                        const uint32_t u4raw = tmem_ld_x1(tm_lane + TM_R4 + ((R1p - 11) & 3) * 8);
                         tmem_ld_wait();
-                        requant_store<FAST>(ra, s_bias + 0, P.q1, v1, dst1 + 0 * PLANE);
-                        requant_store<FAST>(rb, s_bias + 16, P.q1, v1, dst1 + 1 * PLANE);
-                        requant_store<FAST>(rc, s_bias + 64 + 0, P.q22, v2, dst2 + 2 * PLANE);
-                        requant_store<FAST>(rd, s_bias + 64 + 16, P.q21, v2, dst2 + 0 * PLANE);
-                        requant_store<FAST>(re, s_bias + 112 + 0, P.q31, v3, dst3 + 0 * PLANE);
+                        requant_store<FAST, 0>(ra, P, P.q1, v1, dst1 + 0 * PLANE);
+                        requant_store<FAST, 16>(rb, P, P.q1, v1, dst1 + 1 * PLANE);
+                        requant_store<FAST, 64>(rc, P, P.q22, v2, dst2 + 2 * PLANE);
+                        requant_store<FAST, 80>(rd, P, P.q21, v2, dst2 + 0 * PLANE);
+                        requant_store<FAST, 112>(re, P, P.q31, v3, dst3 + 0 * PLANE);
                         // applyRes_y (cnn.cu:507-523) on the finished C4 accumulator
                         if (row4 >= y0 && row4 < y1 && m < WT && X0 + m < W) {
-                            const int x = sm[OFF_IN + mod_pos(row4, IN_SLOTS) * IN_PITCH + 8 + m];
+                            const int x = sm[OFF_IN + ((R1p - 11) & (IN_SLOTS - 1)) * IN_PITCH + 8 + m];
                             outf[(size_t)row4 * W + X0 + m] = (uint8_t)residual_apply((int)u4raw + P.c4_bias, x, P.c4_mul, P.c4_shift);
                         }
                     } else {
@@ -372,11 +392,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         tmem_ld_x16(d21 + 16, rc);
                         tmem_ld_x16(d32 + 0, rd); tmem_ld_x16(d32 + 16, re);
                         tmem_ld_wait();
-                        requant_store<FAST>(ra, s_bias + 32, P.q1, v1, dst1 + 2 * PLANE);
-                        requant_store<FAST>(rb, s_bias + 48, P.q1, v1, dst1 + 3 * PLANE);
-                        requant_store<FAST>(rc, s_bias + 64 + 32, P.q21, v2, dst2 + 1 * PLANE);
-                        requant_store<FAST>(rd, s_bias + 112 + 16, P.q32, v3, dst3 + 1 * PLANE);
-                        requant_store<FAST>(re, s_bias + 112 + 32, P.q32, v3, dst3 + 2 * PLANE);
+                        requant_store<FAST, 32>(ra, P, P.q1, v1, dst1 + 2 * PLANE);
+                        requant_store<FAST, 48>(rb, P, P.q1, v1, dst1 + 3 * PLANE);
+                        requant_store<FAST, 96>(rc, P, P.q21, v2, dst2 + 1 * PLANE);
+                        requant_store<FAST, 128>(rd, P, P.q32, v3, dst3 + 1 * PLANE);
+                        requant_store<FAST, 144>(re, P, P.q32, v3, dst3 + 2 * PLANE);
                     }
                 }
                 lap(1);
@@ -394,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 lap(3);
             }
             // drain: the MMAs of the last iteration still read smem / write TMEM
-            if (!mbar_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1)) { *s_fail = 1; }
+            warp_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1, lane, s_fail);
             ++ev_mma;
             fence_after_sync();
             worker_bar();
@@ -519,6 +539,7 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     addb(QV_C1, 0, P.q1);
     addb(QV_C2_2, 64, P.q22); addb(QV_C2_1, 64 + 16, P.q21);
     addb(QV_C3_1, 112, P.q31); addb(QV_C3_2, 112 + 16, P.q32);
+    memcpy(P.bias, bias, sizeof(P.bias));
     P.c4_bias = m.L[QV_C4].b[0]; P.c4_mul = m.L[QV_C4].mul; P.c4_shift = m.L[QV_C4].shift;
     cudaError_t e = cudaMalloc(&fm->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fm->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice, st);
@@ -569,6 +590,7 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     const int grid = (int)std::min<long long>(units, fm->sm_count);
     const bool prof = getenv("QV_FUSED_PROFILE") != nullptr;
     P.dbg = nullptr;
+    P.dbg_flags = getenv("QV_FUSED_EXPERIMENT") ? atoi(getenv("QV_FUSED_EXPERIMENT")) : 0;
     if (prof && cudaMalloc(&P.dbg, (size_t)grid * 16 * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
     if (P.dbg) cudaMemsetAsync(P.dbg, 0, (size_t)grid * 16 * sizeof(long long), st);
     if (fm->fast) k_fused<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
