@@ -28,6 +28,7 @@ struct qv_net {
     int dev = 0, batch = 0, H = 0, W = 0;
     cudaStream_t st = nullptr;
     cudaStream_t pst[2] = {nullptr, nullptr};      // pipeline slots of qv_forward_frames_host
+    cudaEvent_t ev_compute = nullptr;              // orders the compute stages of the two slots (shared scratch)
     uint8_t *d_x = nullptr, *d_rec = nullptr;      // InputLayer::x / x_rec   (inference/cnn.cu:433-434)
     uint8_t *d_slot_in[2] = {nullptr, nullptr}, *d_slot_out[2] = {nullptr, nullptr};
     uint8_t *h_pin_in[2] = {nullptr, nullptr}, *h_pin_out[2] = {nullptr, nullptr};
@@ -230,6 +231,7 @@ int qv_destroy(qv_net *net)
         cudaFreeHost(net->h_pin_in[i]); cudaFreeHost(net->h_pin_out[i]);
         if (net->pst[i]) cudaStreamDestroy(net->pst[i]);
     }
+    if (net->ev_compute) cudaEventDestroy(net->ev_compute);
     if (net->st) cudaStreamDestroy(net->st);
     delete net;
     return QV_OK;
@@ -391,13 +393,16 @@ int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int
     int rc = set_device(net);
     if (rc) return rc;
     const size_t fpx = (size_t)net->H * net->W;
-    const int chunk = net->batch;
-    const size_t cbytes = (size_t)chunk * fpx;
+    // Pipeline granularity: about four chunks per call so that the H2D of chunk k+1 and the D2H of chunk
+    // k-1 hide behind the compute of chunk k (a single chunk would serialise copy, compute, copy).
+    const int chunk = std::max(1, std::min(net->batch, (n_frames + 3) / 4));
+    const size_t cbytes = (size_t)net->batch * fpx;
     // Is the caller's memory page-locked already?  Then DMA straight from/to it.
     cudaPointerAttributes ai{}, ao{};
     bool pinned_in = cudaPointerGetAttributes(&ai, h_in) == cudaSuccess && ai.type == cudaMemoryTypeHost;
     bool pinned_out = cudaPointerGetAttributes(&ao, h_out) == cudaSuccess && ao.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    if (!net->ev_compute) QV_CUDA(cudaEventCreateWithFlags(&net->ev_compute, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         if (!net->pst[i]) QV_CUDA(cudaStreamCreateWithFlags(&net->pst[i], cudaStreamNonBlocking));
         if (!net->d_slot_in[i]) QV_CUDA(cudaMalloc(&net->d_slot_in[i], cbytes));
@@ -424,8 +429,12 @@ int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int
         const uint8_t *src = h_in + (size_t)f0 * fpx;
         if (!pinned_in) { memcpy(net->h_pin_in[slot], src, bytes); src = net->h_pin_in[slot]; }
         QV_CUDA(cudaMemcpyAsync(net->d_slot_in[slot], src, bytes, cudaMemcpyHostToDevice, net->pst[slot]));
+        // compute stages run one after the other (they share the handle's scratch and every SM anyway);
+        // only the copies of one slot overlap the compute of the other
+        if (f0 > 0) QV_CUDA(cudaStreamWaitEvent(net->pst[slot], net->ev_compute, 0));
         rc = run_forward(net, net->d_slot_in[slot], net->d_slot_out[slot], c, net->H, net->W, net->pst[slot]);
         if (rc) return rc;
+        QV_CUDA(cudaEventRecord(net->ev_compute, net->pst[slot]));
         uint8_t *dst = pinned_out ? h_out + (size_t)f0 * fpx : net->h_pin_out[slot];
         QV_CUDA(cudaMemcpyAsync(dst, net->d_slot_out[slot], bytes, cudaMemcpyDeviceToHost, net->pst[slot]));
         pend[slot].f0 = f0; pend[slot].c = c;

@@ -574,13 +574,20 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     FusedParams P = fm->proto;
     P.in = d_in; P.out = d_out; P.n_frames = n; P.H = H; P.W = W;
     P.nstrips = (W + WT - 1) / WT;
-    // Row segments: only when whole-column strips alone cannot fill the SMs about twice over; every
-    // segment pays PIPE extra iterations, so never cut below 32 rows.
+    // Row segments.  Units are dealt to the persistent CTAs round-robin, so the makespan is
+    // ceil(units / SMs) * (rows per segment + PIPE) row-iterations; pick the cut that minimises it
+    // (never below 16 rows per segment: every segment pays PIPE iterations of pipeline fill).
     const long long cols = (long long)n * P.nstrips;
     int nseg = 1;
-    if (cols < 2ll * fm->sm_count) {
-        nseg = (int)((2ll * fm->sm_count + cols - 1) / cols);
-        nseg = std::max(1, std::min(nseg, (H + 31) / 32));
+    {
+        long long best = -1;
+        const int max_seg = std::max(1, std::min(H / 16, 256));
+        for (int c = 1; c <= max_seg; ++c) {
+            const int rows = (H + c - 1) / c, real = (H + rows - 1) / rows;
+            const long long waves = (cols * real + fm->sm_count - 1) / fm->sm_count;
+            const long long cost = waves * (rows + PIPE);
+            if (best < 0 || cost < best) { best = cost; nseg = c; }
+        }
     }
     P.seg_rows = (H + nseg - 1) / nseg;
     P.nseg = (H + P.seg_rows - 1) / P.seg_rows;
