@@ -235,3 +235,34 @@ def test_quant_param_file_plus_set_weights(models, tmp_path):
     net.load_data(anchor)
     net.forward_blu()
     assert np.array_equal(net.get_recon(), _oracle(m).forward_blu(anchor))
+
+
+@pytest.mark.parametrize("impl", IMPLS, ids=lambda i: IMPL_NAME[i])
+@pytest.mark.parametrize("case", ["not_127_at_blu", "wraps_to_negative", "big_shift"])
+def test_generic_requant_parameters(models, impl, case):
+    """Quant params for which BLU(blu) != 127 (the fast epilogue's precondition fails): the kernels must fall
+    back to the reference's literal formula, including the (char) wrap of results above 127
+    (inference/mat.cu:291 stores into xwtype=char), which makes hidden activations negative."""
+    import copy
+    m = copy.deepcopy(models[32])
+    q = [list(t) for t in m.qparams]
+    if case == "not_127_at_blu":
+        q[0] = [5000, 100, 12]            # (5000+20)*100 >> 12 = 122
+        q[3] = [7000, 281, 14]            # 120
+    elif case == "wraps_to_negative":
+        q[1] = [8000, 100, 12]            # 195 -> (char) -61
+        q[2] = [9000, 99, 12]             # 217 -> (char) -39
+    else:
+        q[4] = [4526, 115 << 14, 26]      # shift > 24: outside the fast path's packing trick, same scale
+    m.qparams = [tuple(t) for t in q]
+    anchor, _ = synth.make_frames(0xC0FFEE + 9, 2, 70, 131)
+    net = _net(m, 2, 70, 131, api.IMPL_LAYERED)
+    _fused_or_skip(net, impl)
+    net.set_impl(impl)
+    net.load_data(anchor)
+    net.forward_blu()
+    want = _oracle(m).forward_blu(anchor)
+    assert np.array_equal(net.get_recon(), want)
+    if case == "wraps_to_negative":
+        a2 = _oracle(m).forward_taps(anchor[0])[2]
+        assert (a2 < 0).any()             # the case really exercises signed hidden activations
