@@ -144,6 +144,22 @@ QV_API int qv_get_activation(qv_net *net, int which /*1,2,3*/, int8_t *host_out)
 /* model_qfp_HWCN2NCHW_VECT_C   inference/qvrcnn.cu:558-585 */
 QV_API int qv_convert_model_hwcn_to_vect_c(const char *file_in, const char *file_out);
 
+/* ---- quant-parameter solver and float -> int8 model quantiser ----------------- */
+/* adjust_quant(stepw_in, blu_in)   training/quantization.py:55-64 (with mul_shift :5-14, mul_shift_f :15-24,
+   quant_qfp_layer :25-31, quant_qfp_concat :32-49, quant_qfp_last :50-53), same IEEE-754 operation order.
+   stepw_in[6], blu_in[6] (order C1, C2_1, C2_2, C3_1, C3_2, C4) -> rows_out[6][6] =
+   [stepw, ratio, blu_adj, blu_q, mul, shift] per layer, i.e. the content of quant_params<QP>.data. */
+QV_API int qv_solve_quant_params(const double *stepw_in, const double *blu_in, double *rows_out36);
+/* The raw flavour quantNsave also writes: quant_params_cpp_<QP>.data, 6 x struct.pack('6d')
+   (training/quantization.py:93-96). */
+QV_API int qv_write_quant_params_cpp(const char *filename, const double *rows36);
+/* Float weights/biases of one layer -> the int8 / int32 the inference path loads:
+   w_q = clip(round(w / stepw), -128, 127)   (training/model.py:167,201; round = half-to-even like numpy.around)
+   b_q = round(b * ratio / stepw)            (training/quantization.py:104, the integer part of it)
+   w is plain [K][C][R][S] float, n_w = K*C*R*S, n_b = K. */
+QV_API int qv_quantize_layer(const float *w, size_t n_w, const float *b, size_t n_b, double stepw, double ratio,
+                             int8_t *w_q, int32_t *b_q);
+
 /* ---- luma frame I/O + PSNR: vrcnn_data (inference/yuv_data.h:11-27) ---------------------- */
 /* vrcnn_data::read_data   inference/yuv_data.cpp:15-42: luma of the first `frames` frames of
    a YUV 4:2:0 8-bit planar file. */

@@ -30,7 +30,7 @@ ABI_SYMBOLS = (
     "qv_sse_device",
     "qv_set_impl", "qv_get_impl", "qv_launch_count", "qv_get_activation",
     "qv_convert_model_hwcn_to_vect_c", "qv_yuv_read_luma", "qv_yuv_read_frame", "qv_yuv_write_recon",
-    "qv_psnr", "qv_psnr_from_sse",
+    "qv_psnr", "qv_psnr_from_sse", "qv_solve_quant_params", "qv_write_quant_params_cpp", "qv_quantize_layer",
 )
 
 
@@ -83,6 +83,9 @@ def lib():
         L.qv_psnr.restype = C.c_double
         L.qv_psnr_from_sse.argtypes = [C.c_int64, C.c_size_t]
         L.qv_psnr_from_sse.restype = C.c_double
+        L.qv_solve_quant_params.argtypes = [vp, vp, vp]
+        L.qv_write_quant_params_cpp.argtypes = [cp, vp]
+        L.qv_quantize_layer.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_double, C.c_double, vp, vp]
         _lib = L
     return _lib
 
@@ -203,6 +206,32 @@ def read_quant_params(filename) -> np.ndarray:
 
 def convert_model_hwcn_to_vect_c(file_in, file_out) -> None:
     _check(lib().qv_convert_model_hwcn_to_vect_c(_b(file_in), _b(file_out)))
+
+
+def solve_quant_params(stepw_in, blu_in) -> np.ndarray:
+    """adjust_quant (training/quantization.py:55-64): -> rows [6][6] = [stepw, ratio, blu_adj, blu_q, mul, shift]."""
+    a = np.ascontiguousarray(stepw_in, np.float64)
+    b = np.ascontiguousarray(blu_in, np.float64)
+    assert a.size == 6 and b.size == 6
+    out = np.zeros(36, np.float64)
+    _check(lib().qv_solve_quant_params(a.ctypes.data, b.ctypes.data, out.ctypes.data))
+    return out.reshape(6, 6)
+
+
+def write_quant_params_cpp(filename, rows) -> None:
+    r = np.ascontiguousarray(rows, np.float64)
+    assert r.size == 36
+    _check(lib().qv_write_quant_params_cpp(_b(filename), r.ctypes.data))
+
+
+def quantize_layer(w: np.ndarray, b: np.ndarray, stepw: float, ratio: float):
+    """float [K,C,R,S] weights + [K] biases -> (int8 weights, int32 biases) as the inference path loads them."""
+    wf = np.ascontiguousarray(w, np.float32)
+    bf = np.ascontiguousarray(b, np.float32)
+    wq = np.empty(wf.shape, np.int8)
+    bq = np.empty(bf.shape, np.int32)
+    _check(lib().qv_quantize_layer(wf.ctypes.data, wf.size, bf.ctypes.data, bf.size, float(stepw), float(ratio), wq.ctypes.data, bq.ctypes.data))
+    return wq, bq
 
 
 def psnr_from_sse(sse: int, n: int) -> float:

@@ -430,6 +430,127 @@ int qv_convert_model_hwcn_to_vect_c(const char *file_in, const char *file_out)
     return QV_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Quant-parameter solver (training/quantization.py:5-64), re-derived in C++ with the same IEEE-754
+// double operation order so that the 36 numbers match the Python module bit for bit.
+// ---------------------------------------------------------------------------------------
+namespace {
+// python round(): half to even.  nearbyint under the default rounding mode does exactly that.
+double py_round(double v) { return std::nearbyint(v); }
+
+// mul_shift(max_u)   quantization.py:5-14: smallest shift i in [1,27] with 127 < max_u*round(127.5*2^i/max_u)/2^i < 127.5
+void solve_mul_shift(double max_u, double &mul, int &shift)
+{
+    mul = 0;
+    int i = 1;
+    for (; i < 28; ++i) {
+        const double max_int = 127.5 * std::ldexp(1.0, i);
+        if (max_int > max_u) {
+            mul = py_round(max_int / max_u);
+            const double temp = max_u * mul / std::ldexp(1.0, i);
+            if (temp > 127 && temp < 127.5) { shift = i; return; }
+        }
+    }
+    shift = 27;                       // python: `return mul,i` after the loop ends with i == 27
+}
+// mul_shift_f(ratio)   quantization.py:15-24
+void solve_mul_shift_f(double ratio, double &mul, int &shift)
+{
+    mul = 0;
+    for (int i = 10; i < 28; ++i) {
+        const double max_int = std::ldexp(1.0, i);
+        if (max_int > ratio) {
+            const double temp = max_int / ratio;
+            mul = py_round(temp);
+            if (std::fabs(max_int / mul - ratio) < 0.02 * ratio) { shift = i; return; }
+        }
+    }
+    shift = 27;
+}
+void set_row(double *row, double stepw, double ratio, double blu_adj, double blu_q, double mul, int shift)
+{
+    row[0] = stepw; row[1] = ratio; row[2] = blu_adj; row[3] = blu_q; row[4] = mul; row[5] = shift;
+}
+// quant_qfp_layer   quantization.py:25-31
+void solve_layer(double ratio, double stepw, double blu, double *row)
+{
+    double blu_q = py_round(blu * ratio / stepw), mul;
+    int sh;
+    solve_mul_shift(blu_q, mul, sh);
+    const double blu_adj = 127 * std::ldexp(1.0, sh) / mul * stepw / ratio;
+    blu_q = py_round(blu_adj * ratio / stepw);
+    set_row(row, stepw, ratio, blu_adj, blu_q, mul, sh);
+}
+// quant_qfp_concat   quantization.py:32-49
+void solve_concat(double ratio, double stepw1, double blu1, double stepw2, double blu2, double *row1, double *row2)
+{
+    if (blu1 < blu2) blu1 = blu2; else blu2 = blu1;
+    const double blu_q1 = py_round(blu1 * ratio / stepw1), blu_q2 = py_round(blu2 * ratio / stepw2);
+    double mul1, mul2;
+    int sh1, sh2;
+    solve_mul_shift(blu_q1, mul1, sh1);
+    solve_mul_shift(blu_q2, mul2, sh2);
+    if (mul1 / stepw1 / std::ldexp(1.0, sh1) > mul2 / stepw2 / std::ldexp(1.0, sh2))
+        stepw1 = stepw2 * std::ldexp(1.0, sh2) / mul2 * mul1 / std::ldexp(1.0, sh1);
+    else
+        stepw2 = stepw1 * std::ldexp(1.0, sh1) / mul1 * mul2 / std::ldexp(1.0, sh2);
+    const double blu1_adj = 127 * std::ldexp(1.0, sh1) / mul1 * stepw1 / ratio;
+    const double blu2_adj = 127 * std::ldexp(1.0, sh2) / mul2 * stepw2 / ratio;
+    set_row(row1, stepw1, ratio, blu1_adj, blu_q1, mul1, sh1);
+    set_row(row2, stepw2, ratio, blu2_adj, blu_q2, mul2, sh2);
+}
+}  // namespace
+
+int qv_solve_quant_params(const double *stepw_in, const double *blu_in, double *rows)
+{
+    if (!stepw_in || !blu_in || !rows) { set_error("qv_solve_quant_params: null argument"); return QV_ERR_ARG; }
+    for (int l = 0; l < 6; ++l)
+        if (!(stepw_in[l] > 0) || (l < 5 && !(blu_in[l] > 0))) { set_error("qv_solve_quant_params: stepw and blu must be positive (layer %d)", l); return QV_ERR_ARG; }
+    double ratio = 255;                                                       // quantization.py:56
+    solve_layer(ratio, stepw_in[0], blu_in[0], rows);
+    ratio = ratio / rows[0] * rows[4] / std::ldexp(1.0, (int)rows[5]);        // :58
+    solve_concat(ratio, stepw_in[1], blu_in[1], stepw_in[2], blu_in[2], rows + 6, rows + 12);
+    ratio = ratio / rows[6] * rows[6 + 4] / std::ldexp(1.0, (int)rows[6 + 5]); // :60
+    solve_concat(ratio, stepw_in[3], blu_in[3], stepw_in[4], blu_in[4], rows + 18, rows + 24);
+    ratio = ratio / rows[18] * rows[18 + 4] / std::ldexp(1.0, (int)rows[18 + 5]);   // :62
+    {                                                                         // quant_qfp_last :50-53
+        double mul;
+        int sh;
+        solve_mul_shift_f(ratio / 255 / stepw_in[5], mul, sh);
+        const double stepw_adj = ratio * mul / std::ldexp(1.0, sh) / 255;
+        set_row(rows + 30, stepw_adj, ratio, 0, 0, mul, sh);
+    }
+    return QV_OK;
+}
+
+int qv_write_quant_params_cpp(const char *filename, const double *rows)
+{
+    if (!rows) { set_error("qv_write_quant_params_cpp: null argument"); return QV_ERR_ARG; }
+    FILE *fp = filename ? fopen(filename, "wb") : nullptr;
+    if (!fp) { set_error("cannot open %s for writing", filename ? filename : "(null)"); return QV_ERR_IO; }
+    const size_t put = fwrite(rows, sizeof(double), 36, fp);
+    fclose(fp);
+    if (put != 36) { set_error("short write on %s", filename); return QV_ERR_IO; }
+    return QV_OK;
+}
+
+int qv_quantize_layer(const float *w, size_t n_w, const float *b, size_t n_b, double stepw, double ratio, int8_t *w_q, int32_t *b_q)
+{
+    if (!w || !b || !w_q || !b_q || !(stepw > 0)) { set_error("qv_quantize_layer: bad argument"); return QV_ERR_ARG; }
+    for (size_t i = 0; i < n_w; ++i) {
+        // numpy: np.clip(np.around(wf / stepw), -128, 127); wf is float32, stepw a python float -> float64 division
+        double q = py_round((double)w[i] / stepw);
+        q = q < -128 ? -128 : (q > 127 ? 127 : q);
+        w_q[i] = (int8_t)q;
+    }
+    for (size_t i = 0; i < n_b; ++i) {
+        const double q = py_round((double)b[i] * ratio / stepw);
+        if (!(std::fabs(q) < 2147483647.0)) { set_error("qv_quantize_layer: bias %zu does not fit int32", i); return QV_ERR_RANGE; }
+        b_q[i] = (int32_t)q;
+    }
+    return QV_OK;
+}
+
 int qv_yuv_read_luma(const char *filename, int frames, int height, int width, uint8_t *out)
 {
     if (!out || frames < 0 || height <= 0 || width <= 0) { set_error("qv_yuv_read_luma: bad argument"); return QV_ERR_ARG; }
