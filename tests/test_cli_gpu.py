@@ -1,0 +1,58 @@
+"""The reference's driver surface (inference/kernel.cu:74-138, run_all.bat): `qcnn_gpu <ori.yuv>
+<anchor_prefix> <H> <W>` on YUV 4:2:0 files, report lines, log.txt / recon_psnr.data appends."""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from qcnn_gpu_b200.host import formats, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "qcnn_gpu_b200", "qcnn_gpu")
+
+
+def _write_yuv(path, luma, chroma_value):
+    with open(path, "wb") as fp:
+        for f in range(luma.shape[0]):
+            fp.write(luma[f].tobytes())
+            fp.write(bytes([chroma_value]) * (luma.shape[1] * luma.shape[2] // 2))
+
+
+@pytest.mark.parametrize("frames,gpus", [(1, 1), (3, 1)])
+def test_cli_matches_oracle_report(tmp_path, models, frames, gpus):
+    from oracle import oracle
+    qp, h, w = 37, 64, 112
+    anchor, ori = synth.make_frames(0xC0FFEE + 11, frames, h, w)
+    _write_yuv(tmp_path / "ori.yuv", ori, 0x80)
+    _write_yuv(tmp_path / ("anchor_Q%d.yuv" % qp), anchor, 0x33)
+    (tmp_path / ("model_%d.data" % qp)).write_bytes(formats.write_model_vect_c(models[qp]))
+    assert os.path.exists(CLI), "qcnn_gpu CLI not built"
+    p = subprocess.run([CLI, "ori.yuv", "anchor_", str(h), str(w), "--model", "model_%d.data", "--qp", str(qp),
+                        "--frames", str(frames), "--gpus", str(gpus), "--save-recon", "recon.yuv"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    want = oracle.OracleModel(formats.write_model_vect_c(models[qp])).forward_blu(anchor)
+    before = float(re.search(r"before net:PSNR=([0-9.]+)", p.stdout).group(1))
+    after = float(re.search(r"after quantized net:PSNR=([0-9.]+)", p.stdout).group(1))
+    assert before == pytest.approx(round(oracle.psnr(anchor, ori)[0], 3), abs=1.1e-3)
+    assert after == pytest.approx(round(oracle.psnr(want, ori)[0], 3), abs=1.1e-3)
+    # recon file: Y plane + zeroed chroma (inference/yuv_data.cpp:119-125), luma identical to the oracle
+    raw = np.frombuffer((tmp_path / "recon.yuv").read_bytes(), np.uint8).reshape(frames, h * w * 3 // 2)
+    assert np.array_equal(raw[:, :h * w].reshape(frames, h, w), want)
+    assert not raw[:, h * w:].any()
+    # appended artefacts of kernel.cu:107-115
+    assert "after quantized net:PSNR=" in (tmp_path / "log.txt").read_text()
+    (psnr2,) = struct.unpack("<d", (tmp_path / "recon_psnr.data").read_bytes())
+    assert psnr2 == oracle.psnr(want, ori)[0]
+
+
+def test_cli_missing_model_exits_like_the_reference(tmp_path):
+    anchor, ori = synth.make_frames(1, 1, 16, 16)
+    _write_yuv(tmp_path / "ori.yuv", ori, 0)
+    _write_yuv(tmp_path / "a_Q22.yuv", anchor, 0)
+    p = subprocess.run([CLI, "ori.yuv", "a_", "16", "16", "--model", "nope_%d.data"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 1 and "cannot open model file." in p.stdout        # inference/qvrcnn.cu:50-54
