@@ -233,12 +233,10 @@ static cudaError_t launch_conv(const int8_t *in, int8_t *out, const LayeredLayer
 {
     constexpr int TH = TY + KS - 1, TW = TX + KS - 1, C4 = CIN / 4;
     const size_t smem = sizeof(int32_t) * (size_t)(C4 * TH * TW + KS * KS * C4 * 16);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv<CIN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // function attributes are per device: set it on every launch (a few hundred ns) so that handles on
+    // several GPUs of one process all get it
+    cudaError_t e = cudaFuncSetAttribute(k_conv<CIN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const int ngroups = L.cout / 16;
     dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, n * ngroups), block(TX, TY);
     k_conv<CIN, KS><<<grid, block, smem, st>>>(in, out, L.d_wpk, L.d_bias, L.q, H, W, out_ch, out_coff, ngroups);
