@@ -44,35 +44,53 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one streaming nvidia-smi
+    process at 50 ms period; only lines that arrive between start() and stop() are kept)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.samples, self.stop_flag, self.proc = index, [], threading.Event(), None
 
     def run(self):
-        while not self.stop_flag.is_set():
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                parts = [s.strip() for s in line.split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                self.proc.terminate()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+        self.join(timeout=2)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(s[0]) for s in self.samples if num(s[0]) is not None]
+        mx = [num(s[1]) for s in self.samples if num(s[1]) is not None]
+        pw = [num(s[2]) for s in self.samples if num(s[2]) is not None]
         reasons = set()
         for s in self.samples:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
 def build_inputs(rank: int):
@@ -214,6 +232,8 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(0.15)                             # let the sampler's nvidia-smi come up; the GPU idles meanwhile
+    sampler.samples.clear()
     l0 = net.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record(stream)
@@ -222,8 +242,7 @@ def main():
         evs[i + 1].record(stream)
     barrier()
     launches = net.launch_count() - l0
-    sampler.stop_flag.set()
-    sampler.join()
+    sampler.stop()
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
 

@@ -393,9 +393,25 @@ int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int
     int rc = set_device(net);
     if (rc) return rc;
     const size_t fpx = (size_t)net->H * net->W;
-    // Pipeline granularity: about four chunks per call so that the H2D of chunk k+1 and the D2H of chunk
-    // k-1 hide behind the compute of chunk k (a single chunk would serialise copy, compute, copy).
-    const int chunk = std::max(1, std::min(net->batch, (n_frames + 3) / 4));
+    // Pipeline granularity: the H2D of chunk k+1 and the D2H of chunk k-1 hide behind the compute of chunk k;
+    // only the first upload and the last download are exposed, so the schedule is tapered -- small chunks at
+    // both ends (1/16, 3/16, 1/4, 1/4, 3/16, 1/16 of the frames), each at most `batch` frames.
+    std::vector<int> chunks;
+    {
+        static const int num[6] = {1, 3, 4, 4, 3, 1};
+        int left = n_frames;
+        if (n_frames >= 16) {
+            for (int k = 0; k < 6 && left > 0; ++k) {
+                int want = k == 5 ? left : std::max(1, n_frames * num[k] / 16);
+                while (want > 0 && left > 0) {
+                    const int c = std::min(std::min(want, left), net->batch);
+                    chunks.push_back(c); want -= c; left -= c;
+                }
+            }
+        }
+        const int uni = std::max(1, std::min(net->batch, (n_frames + 3) / 4));
+        while (left > 0) { const int c = std::min(uni, left); chunks.push_back(c); left -= c; }
+    }
     const size_t cbytes = (size_t)net->batch * fpx;
     // Is the caller's memory page-locked already?  Then DMA straight from/to it.
     cudaPointerAttributes ai{}, ao{};
@@ -422,8 +438,9 @@ int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int
         return QV_OK;
     };
     int slot = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += chunk, slot ^= 1) {
-        const int c = std::min(chunk, n_frames - f0);
+    int f0 = 0;
+    for (size_t ci = 0; ci < chunks.size(); f0 += chunks[ci], ++ci, slot ^= 1) {
+        const int c = chunks[ci];
         const size_t bytes = (size_t)c * fpx;
         if ((rc = drain(slot))) return rc;
         const uint8_t *src = h_in + (size_t)f0 * fpx;
