@@ -227,12 +227,11 @@ def main():
     def step_device():
         net.forward_frames_device(d_in.data_ptr(), d_out.data_ptr(), FRAMES, stream.cuda_stream)
 
+    sampler = ClockSampler(local)
+    sampler.start()                              # comes up during the warm-up; its samples are cleared below
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.15)                             # let the sampler's nvidia-smi come up; the GPU idles meanwhile
     sampler.samples.clear()
     l0 = net.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
