@@ -51,35 +51,35 @@ constexpr int WT = 120;                    // output columns per strip
 constexpr int PW = 136;                    // pixel pitch of every activation row buffer
 constexpr int PLANE = PW * 16;             // bytes of one 16-channel plane of one row
 constexpr int A_SLOTS = 3, IN_SLOTS = 32, IN_PITCH = 144;
-constexpr int A1_ROW = 4 * PLANE, A2_ROW = 3 * PLANE, A3_ROW = 3 * PLANE;
+constexpr int A1_ROW = 4 * PLANE, A2_ROW = 3 * PLANE;
 constexpr int IM_BYTES = 2 * 128 * 16;     // one im2col A operand for C1: [2 K-planes][128 px][16 B]
 constexpr int ZERO_BYTES = 2 * 128 * 16;   // all-zero A operand (ring-slot initialisation)
 
 // ---- B operands (weights) in smem: every block is [2 K-chunks][NR rows][16 B] ---------------------
-constexpr int NR22 = 11 * 16, NR21 = 7 * 32, NR31 = 7 * 16, NR32 = 32, NR4 = 7 * 8;
+constexpr int NR22 = 11 * 16, NR21 = 7 * 32, NR31 = 7 * 16, NR32 = 32;
 constexpr int W1_BYTES = 2 * 64 * 16;
-constexpr int T22 = 2 * NR22 * 16, T21 = 2 * NR21 * 16, T31 = 2 * NR31 * 16, T32 = 2 * NR32 * 16, T4 = 2 * NR4 * 16;
+constexpr int T22 = 2 * NR22 * 16, T21 = 2 * NR21 * 16, T31 = 2 * NR31 * 16, T32 = 2 * NR32 * 16;
 constexpr int OFF_W1 = 0;
 constexpr int OFF_W22 = OFF_W1 + W1_BYTES;      // 10 tiles (s, h)
 constexpr int OFF_W21 = OFF_W22 + 10 * T22;     //  6 tiles (s', h)
 constexpr int OFF_W31 = OFF_W21 + 6 * T21;      //  5 K-steps
 constexpr int OFF_W32 = OFF_W31 + 5 * T31;      //  2 K-steps
-constexpr int OFF_W4 = OFF_W32 + 2 * T32;       //  5 K-steps
-constexpr int OFF_BIAS = OFF_W4 + 5 * T4;
+constexpr int OFF_BIAS = OFF_W32 + 2 * T32;
 constexpr int BIAS_INTS = 64 + 48 + 48;
 constexpr int WIMG_BYTES = OFF_BIAS + BIAS_INTS * 4;         // what lives in global memory per model
 constexpr int OFF_A1 = (WIMG_BYTES + 127) / 128 * 128;
 constexpr int OFF_A2 = OFF_A1 + A_SLOTS * A1_ROW;
-constexpr int OFF_A3 = OFF_A2 + A_SLOTS * A2_ROW;
-constexpr int OFF_IM = OFF_A3 + A_SLOTS * A3_ROW;
+constexpr int OFF_IM = OFF_A2 + A_SLOTS * A2_ROW;
 constexpr int OFF_ZERO = OFF_IM + 2 * IM_BYTES;
 constexpr int OFF_IN = OFF_ZERO + ZERO_BYTES;
-constexpr int OFF_CTRL = OFF_IN + IN_SLOTS * IN_PITCH;
+constexpr int PART_ROW = 9 * PW * 4;                 // C4 partial dot products of one a3 row: [tap][pixel] int32
+constexpr int OFF_PART = OFF_IN + IN_SLOTS * IN_PITCH;     // [iteration parity][warp half][tap][pixel]
+constexpr int OFF_CTRL = OFF_PART + 2 * 2 * PART_ROW;
 constexpr int SMEM_BYTES = OFF_CTRL + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
 constexpr int NWORKER = 256, NTHREADS = NWORKER + 32;
-constexpr int PIPE = 15;                   // pipeline depth in rows: output row y0 appears at iteration 15
+constexpr int PIPE = 14;                   // pipeline depth in rows: output row y0 appears at iteration 14
 
 // ---- TMEM columns (int32 accumulators) -------------------------------------------------------------
 constexpr int TM_D1 = 0;        // C1: 2 x 64, double-buffered by iteration parity
@@ -87,7 +87,6 @@ constexpr int TM_R22 = 128;     // C2_2 ring: 6 slots x 16
 constexpr int TM_R21 = 224;     // C2_1 ring: 4 slots x 32
 constexpr int TM_R31 = 352;     // C3_1 ring: 4 slots x 16
 constexpr int TM_D32 = 416;     // C3_2: 2 x 32, double-buffered
-constexpr int TM_R4 = 480;      // C4 ring: 4 slots x 8 (column 0 of each slot is the residual accumulator)
 constexpr int TM_COLS = 512;
 
 // Per 16-column accumulator group: everything the requantiser needs.
@@ -104,6 +103,7 @@ struct FusedParams {
     int n_frames, H, W, nstrips, nseg, seg_rows, n_units;
     GroupQ q1, q22, q21, q31, q32;
     int c4_bias, c4_mul, c4_shift;
+    int c4_w[108];                     // C4 weights [tap][plane][4 words], 4 channels per word (CUDA-core dp4a)
     long long *dbg;                    // optional per-block phase timers (QV_FUSED_PROFILE=1), else null
     int dbg_flags;                     // tuning experiments only (QV_FUSED_EXPERIMENT): 1 = issue no MMAs, 2 = workers skip the drains
     int bias[BIAS_INTS];               // per accumulator column: layer bias (+ rounding bias on the FAST path)
@@ -128,10 +128,9 @@ __device__ __forceinline__ void warp_wait(uint64_t *bar, uint32_t parity, int la
 // ---- requantise 16 accumulator columns of this thread's pixel and store them as one 16-byte
 // ---- channel group of an activation row (mat.cu:262-303 folded into the TMEM epilogue)
 template <bool FAST, int BOFF>
-__device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const FusedParams &P, const GroupQ &g, bool valid,
-                                              uint8_t *dst)
+__device__ __forceinline__ void requant(const uint32_t (&r)[16], const FusedParams &P, const GroupQ &g, bool valid,
+                                        uint32_t (&o)[4])
 {
-    uint32_t o[4];
     const unsigned Mz = valid ? g.M : 0u;           // FAST: an out-of-image pixel multiplies by 0
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -153,7 +152,23 @@ __device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const Fus
         // gather the four top bytes into one word
         o[v] = __byte_perm(__byte_perm(q[0], q[1], 0x0073), __byte_perm(q[2], q[3], 0x0073), 0x5410);
     }
+}
+template <bool FAST, int BOFF>
+__device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const FusedParams &P, const GroupQ &g, bool valid,
+                                              uint8_t *dst)
+{
+    uint32_t o[4];
+    requant<FAST, BOFF>(r, P, g, valid, o);
     *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+// C4 (48 -> 1, 3x3) partial dot products of one pixel's 16 a3 channels (plane PL) with all nine taps
+template <int PL>
+__device__ __forceinline__ void c4_partials(const uint32_t (&o)[4], const FusedParams &P, int (&acc)[9])
+{
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[t] = __dp4a((int)o[j], P.c4_w[(t * 3 + PL) * 4 + j], acc[t]);
 }
 
 template <bool FAST>
@@ -198,88 +213,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         const bool leader = elect_one();
         uint32_t ev_work = 0, ev_mma = 0;
         long long t_wait = 0, t_issue = 0, tc0 = clock64();
-        constexpr uint32_t HI = (128u >> 4) | (1u << 14);                     // SBO = 128 B, descriptor version 1
-        auto desc = [](uint32_t addr_bytes, uint32_t lbo_bytes) {
-            return ((uint64_t)HI << 32) | (uint64_t)(((addr_bytes >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16));
-        };
+        // Descriptors are handled as their low 32-bit word in 16-byte units: (smem address >> 4) | (LBO >> 4) << 16;
+        // the high word (SBO = 128 B, version 1) is a constant.  Everything that changes per iteration is
+        // computed up front, so that between two MMAs there is one add per operand: the tensor-pipe queue
+        // is short, and a long scalar stretch in this warp drains it.
+        constexpr uint64_t HI = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+        constexpr uint32_t LP = (uint32_t)(PLANE >> 4) << 16;                  // LBO = one plane: K-halves are planes p, p+1
+        constexpr uint32_t LX = 1u << 16;                                      // LBO = 16 B: K-halves are pixels x, x+1 of one plane
         const bool issue = leader && !(P.dbg_flags & 1);
-        auto MMA = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-            if (issue) mma_i8_ss(d, a, b, idesc, acc);
+        auto MMA = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+            if (issue) mma_i8_ss(d, HI | a_lo, HI | b_lo, idesc, acc);
         };
-        const uint64_t zeroA = desc(sbase + OFF_ZERO, 128 * 16);
-        const uint64_t anyB16 = desc(sbase + OFF_W1, 64 * 16);
+        const uint32_t sb = sbase >> 4;
+        const uint32_t zeroA = sb + (OFF_ZERO >> 4) + ((128u * 16 >> 4) << 16);
+        const uint32_t anyB = sb + (OFF_W1 >> 4) + (64u << 16);
+        const uint32_t w1 = sb + (OFF_W1 >> 4) + (64u << 16);
+        const uint32_t w22 = sb + (OFF_W22 >> 4) + ((uint32_t)NR22 << 16), w21 = sb + (OFF_W21 >> 4) + ((uint32_t)NR21 << 16);
+        const uint32_t w31 = sb + (OFF_W31 >> 4) + ((uint32_t)NR31 << 16), w32 = sb + (OFF_W32 >> 4) + ((uint32_t)NR32 << 16);
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg;
             const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
-                const int R1 = y0 - 4 + i, R1p = R1 + 4096;
+                const int R1p = y0 - 4 + i + 4096;
+                const uint32_t par = i & 1;
+                // ---- everything that depends on the iteration -----------------------------------------
+                const int qa = wrap_sub(c6, 2, 6);                                            // (R1-2) mod 6
+                const uint32_t a1_r2 = sb + (OFF_A1 >> 4) + wrap_sub(c3, 2, 3) * (A1_ROW >> 4) + LP;   // a1 row R1-2 (C2_2)
+                const uint32_t a1_r3 = sb + (OFF_A1 >> 4) + c3 * (A1_ROW >> 4) + LP;                   // a1 row R1-3 (C2_1)
+                const uint32_t a2_r6 = sb + (OFF_A2 >> 4) + c3 * (A2_ROW >> 4);                        // a2 row R1-6 (C3_1)
+                const uint32_t a2_r7 = sb + (OFF_A2 >> 4) + wrap_sub(c3, 7, 3) * (A2_ROW >> 4);        // a2 row R1-7 (C3_2)
+                const uint32_t b22 = w22 + (qa <= 2 ? 2 - qa : 8 - qa) * 16;         // window start (8 - qa) mod 6 blocks of 16 rows
+                const uint32_t b21 = w21 + ((1 - (R1p - 3)) & 3) * 32;               // (1 - (R1-3) mod 4) mod 4 blocks of 32 rows
+                const uint32_t b31 = w31 + ((1 - (R1p - 6)) & 3) * 16;
+                const uint32_t d1 = tm + TM_D1 + par * 64, d32 = tm + TM_D32 + par * 32;
+                const uint32_t z22 = tm + TM_R22 + c6 * 16;                          // C2_2 row R1   starts: zero its slot
+                const uint32_t z21 = tm + TM_R21 + ((R1p - 2) & 3) * 32;             // C2_1 row R1-2 starts
+                const uint32_t z31 = tm + TM_R31 + ((R1p - 5) & 3) * 16;             // C3_1 row R1-5 starts
+                const uint32_t im = sb + ((OFF_IM + par * IM_BYTES) >> 4) + ((128u * 16 >> 4) << 16);
                 warp_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1, lane, s_fail);
                 ++ev_work;
                 fence_after_sync();
                 { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
-                const uint32_t par = i & 1;
-                // ---- C1: a1 row R1 = im2col[par] x W1 (N = 64) --------------------------------
-                MMA(tm + TM_D1 + par * 64, desc(sbase + OFF_IM + par * IM_BYTES, 128 * 16), desc(sbase + OFF_W1, 64 * 16),
-                    idesc_i8(128, 64), 0);
-                // ---- C2_2 (5x5, 64 -> 16): scatter a1 row Ra into the 6-slot ring, N = 96 ----------
-                {
-                    const uint32_t arow = sbase + OFF_A1 + wrap_sub(c3, 2, 3) * A1_ROW;          // a1 row Ra = R1-2
-                    const int qa = wrap_sub(c6, 2, 6);                                           // Ra mod 6
-                    const uint32_t boff = (qa <= 2 ? 2 - qa : 8 - qa) * 16 * 16;                 // window start (8 - qa) mod 6, 16 rows per block
-                    MMA(tm + TM_R22 + c6 * 16, zeroA, anyB16, idesc_i8(128, 16), 0);             // row Ra+2 = R1 starts
+                // ---- C1: a1 row R1 = im2col[par] x W1 (N = 64) --------------------------------------
+                MMA(d1, im, w1, idesc_i8(128, 64), 0);
+                // ---- C2_2 (5x5, 64 -> 16): scatter a1 row R1-2 into the 6-slot ring, N = 96 -----------
+                MMA(z22, zeroA, anyB, idesc_i8(128, 16), 0);
 #pragma unroll
-                    for (int s = 0; s < 5; ++s)
+                for (int t = 0; t < 10; ++t)             // t = s*2 + h: shift s = pixel 4+s, K-half h = planes 2h, 2h+1
+                    MMA(tm + TM_R22, a1_r2 + (((t & 1) * 2 * PLANE + (4 + t / 2) * 16) >> 4), b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
+                // ---- C2_1 (3x3, 64 -> 32): scatter a1 row R1-3 into the 4-slot ring, N = 128 -----------
+                MMA(z21, zeroA, anyB, idesc_i8(128, 32), 0);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            MMA(tm + TM_R22, desc(arow + h * 2 * PLANE + (4 + s) * 16, PLANE),
-                                desc(sbase + OFF_W22 + (s * 2 + h) * T22 + boff, NR22 * 16), idesc_i8(128, 96), 1);
-                }
-                // ---- C2_1 (3x3, 64 -> 32): scatter a1 row R1-3 into the 4-slot ring, N = 128 ---------
-                {
-                    const uint32_t arow = sbase + OFF_A1 + c3 * A1_ROW;                          // a1 row Ra = R1-3 (== R1 mod 3)
-                    const uint32_t boff = ((1 - (R1p - 3)) & 3) * 32 * 16;                       // (1 - Ra mod 4) mod 4
-                    MMA(tm + TM_R21 + ((R1p - 2) & 3) * 32, zeroA, anyB16, idesc_i8(128, 32), 0);  // row Ra+1 starts
+                for (int t = 0; t < 6; ++t)
+                    MMA(tm + TM_R21, a1_r3 + (((t & 1) * 2 * PLANE + (5 + t / 2) * 16) >> 4), b21 + t * (T21 >> 4), idesc_i8(128, 128), 1);
+                // ---- C3_1 (3x3, 48 -> 16): scatter a2 row R1-6 into the 4-slot ring, N = 64.  K-steps pair 16-channel
+                //      units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights) ----------------
+                MMA(z31, zeroA, anyB, idesc_i8(128, 16), 0);
 #pragma unroll
-                    for (int s = 0; s < 3; ++s)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            MMA(tm + TM_R21, desc(arow + h * 2 * PLANE + (5 + s) * 16, PLANE),
-                                desc(sbase + OFF_W21 + (s * 2 + h) * T21 + boff, NR21 * 16), idesc_i8(128, 128), 1);
-                }
-                // ---- C3_1 (3x3, 48 -> 16): scatter a2 row Rb into the 4-slot ring, N = 64.  K-steps pair
-                //      16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights)
-                {
-                    const uint32_t arow = sbase + OFF_A2 + c3 * A2_ROW;                          // a2 row Rb = R1-6
-                    const uint32_t boff = ((1 - (R1p - 6)) & 3) * 16 * 16;
-                    MMA(tm + TM_R31 + ((R1p - 5) & 3) * 16, zeroA, anyB16, idesc_i8(128, 16), 0);
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const uint64_t a = k < 3 ? desc(arow + (6 + k) * 16, PLANE)
-                                                 : desc(arow + 2 * PLANE + (k == 3 ? 6 : 8) * 16, 16);
-                        MMA(tm + TM_R31, a, desc(sbase + OFF_W31 + k * T31 + boff, NR31 * 16), idesc_i8(128, 64), 1);
-                    }
-                }
-                // ---- C3_2 (1x1, 48 -> 32) of a2 row R1-7, N = 32 ------------------------------------
-                {
-                    const uint32_t arow = sbase + OFF_A2 + wrap_sub(c3, 7, 3) * A2_ROW;
-                    MMA(tm + TM_D32 + par * 32, desc(arow + 7 * 16, PLANE), desc(sbase + OFF_W32, NR32 * 16), idesc_i8(128, 32), 0);
-                    MMA(tm + TM_D32 + par * 32, desc(arow + 2 * PLANE + 7 * 16, 16), desc(sbase + OFF_W32 + T32, NR32 * 16),
-                        idesc_i8(128, 32), 1);
-                }
-                // ---- C4 (3x3, 48 -> 1): scatter a3 row Rc into the 4-slot ring of 8-column slots, N = 32 ---
-                {
-                    const uint32_t arow = sbase + OFF_A3 + c3 * A3_ROW;                          // a3 row Rc = R1-9
-                    const uint32_t boff = ((1 - (R1p - 9)) & 3) * 8 * 16;
-                    MMA(tm + TM_R4 + ((R1p - 8) & 3) * 8, zeroA, anyB16, idesc_i8(128, 8), 0);
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const uint64_t a = k < 3 ? desc(arow + (7 + k) * 16, PLANE)
-                                                 : desc(arow + 2 * PLANE + (k == 3 ? 7 : 9) * 16, 16);
-                        MMA(tm + TM_R4, a, desc(sbase + OFF_W4 + k * T4 + boff, NR4 * 16), idesc_i8(128, 32), 1);
-                    }
-                }
+                for (int k = 0; k < 5; ++k)
+                    MMA(tm + TM_R31, k < 3 ? a2_r6 + 6 + k + LP : a2_r6 + ((2 * PLANE) >> 4) + (k == 3 ? 6 : 8) + LX, b31 + k * (T31 >> 4),
+                        idesc_i8(128, 64), 1);
+                // ---- C3_2 (1x1, 48 -> 32) of a2 row R1-7, N = 32 --------------------------------------
+                MMA(d32, a2_r7 + 7 + LP, w32, idesc_i8(128, 32), 0);
+                MMA(d32, a2_r7 + ((2 * PLANE) >> 4) + 7 + LX, w32 + (T32 >> 4), idesc_i8(128, 32), 1);
                 if (leader) mma_commit(&bar_mma[ev_mma & 1]);
                 ++ev_mma;
                 __syncwarp();
@@ -341,6 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 ++ev_work;
             }
             int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
+            int c4_s1 = 0, c4_s2 = 0;
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
                 const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
@@ -355,38 +354,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     fence_after_sync();
                     lap(0);
                     const uint32_t par = (i - 1) & 1;
-                    // ---- drain what iteration i-1 completed.  Ten 16-column groups, five per warp half:
+                    // ---- (A) output row R1-10: C4 = the nine-tap sum of the per-pixel partial dot products that both
+                    //      warp halves left in smem for a3 row R1-9 one iteration ago, accumulated over three rows in
+                    //      two registers (s1: row above started, s2: row above + this row), then applyRes_y.
+                    if (hh == 0 && i >= 2) {
+                        const int *part = reinterpret_cast<const int *>(sm + OFF_PART + ((i - 1) & 1) * 2 * PART_ROW) + 8 + m;
+                        int q[3];
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            int v = 0;
+#pragma unroll
+                            for (int sft = 0; sft < 3; ++sft)
+                                v += part[(r * 3 + sft) * PW + sft - 1] + part[(9 + r * 3 + sft) * PW + sft - 1];
+                            q[r] = v;
+                        }
+                        const int u4 = c4_s2 + q[2];              // out row y: a3 rows y-1 (tap row 0), y (1), y+1 (2)
+                        c4_s2 = c4_s1 + q[1];
+                        c4_s1 = q[0];
+                        const int rowo = R1 - 10;
+                        if (rowo >= y0 && rowo < y1 && m < WT && X0 + m < W) {
+                            const int x = sm[OFF_IN + ((R1p - 10) & (IN_SLOTS - 1)) * IN_PITCH + 8 + m];
+                            outf[(size_t)rowo * W + X0 + m] = (uint8_t)residual_apply(u4 + P.c4_bias, x, P.c4_mul, P.c4_shift);   // cnn.cu:507-523
+                        }
+                    }
+                    // ---- (B) drain what iteration i-1 completed.  Ten 16-column groups, five per warp half:
                     //      a1 row R1-1 : D1[par] groups 0..3                      -> a1 planes 0..3
                     //      a2 row R1-5 : C2_2 ring slot (16) -> plane 2 ; C2_1 ring slot (32) -> planes 0,1
-                    //      a3 row R1-8 : C3_1 ring slot (16) -> plane 0 ; C3_2 D32[par] (32)   -> planes 1,2
-                    //      out row R1-11: C4 ring slot, column 0 (warp half 0)
-                    const int row1 = R1 - 1, row2 = R1 - 5, row3 = R1 - 8, row4 = R1 - 11;
+                    //      a3 row R1-8 : C3_1 ring slot (16) = channels 0..15 ; C3_2 D32[par] (32) = channels 16..47.
+                    //      a3 is never stored: its only consumer, C4 (48 -> 1), is nine dp4a partial sums per pixel and
+                    //      16 channels taken straight from the requantised registers.
+                    const int row1 = R1 - 1, row2 = R1 - 5, row3 = R1 - 8;
                     const bool v1 = row1 >= 0 && row1 < H && X0 - 4 + m >= 0 && X0 - 4 + m < W;
                     const bool v2 = row2 >= 0 && row2 < H && X0 - 2 + m >= 0 && X0 - 2 + m < W;
                     const bool v3 = row3 >= 0 && row3 < H && X0 - 1 + m >= 0 && X0 - 1 + m < W;
                     uint8_t *dst1 = sm + OFF_A1 + wrap_sub(c3, 1, 3) * A1_ROW + (4 + m) * 16;
                     uint8_t *dst2 = sm + OFF_A2 + wrap_sub(c3, 5, 3) * A2_ROW + (6 + m) * 16;
-                    uint8_t *dst3 = sm + OFF_A3 + wrap_sub(c3, 8, 3) * A3_ROW + (7 + m) * 16;
+                    int *pdst = reinterpret_cast<int *>(sm + OFF_PART + (i & 1) * 2 * PART_ROW + hh * PART_ROW) + 7 + m;
                     const uint32_t d1 = tm_lane + TM_D1 + par * 64;
                     const uint32_t d22 = tm_lane + TM_R22 + wrap_sub(c6, 5, 6) * 16, d21 = tm_lane + TM_R21 + ((R1p - 5) & 3) * 32;
                     const uint32_t d31 = tm_lane + TM_R31 + ((R1p - 8) & 3) * 16, d32 = tm_lane + TM_D32 + par * 32;
-                    uint32_t ra[16], rb[16], rc[16], rd[16], re[16];
+                    uint32_t ra[16], rb[16], rc[16], rd[16], re[16], o[4];
+                    int acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                     if (hh == 0) {
                         tmem_ld_x16(d1 + 0, ra); tmem_ld_x16(d1 + 16, rb);
                         tmem_ld_x16(d22, rc); tmem_ld_x16(d21, rd);
                         tmem_ld_x16(d31, re);
-                        const uint32_t u4raw = tmem_ld_x1(tm_lane + TM_R4 + ((R1p - 11) & 3) * 8);
                         tmem_ld_wait();
                         requant_store<FAST, 0>(ra, P, P.q1, v1, dst1 + 0 * PLANE);
                         requant_store<FAST, 16>(rb, P, P.q1, v1, dst1 + 1 * PLANE);
                         requant_store<FAST, 64>(rc, P, P.q22, v2, dst2 + 2 * PLANE);
                         requant_store<FAST, 80>(rd, P, P.q21, v2, dst2 + 0 * PLANE);
-                        requant_store<FAST, 112>(re, P, P.q31, v3, dst3 + 0 * PLANE);
-                        // applyRes_y (cnn.cu:507-523) on the finished C4 accumulator
-                        if (row4 >= y0 && row4 < y1 && m < WT && X0 + m < W) {
-                            const int x = sm[OFF_IN + ((R1p - 11) & (IN_SLOTS - 1)) * IN_PITCH + 8 + m];
-                            outf[(size_t)row4 * W + X0 + m] = (uint8_t)residual_apply((int)u4raw + P.c4_bias, x, P.c4_mul, P.c4_shift);
-                        }
+                        requant<FAST, 112>(re, P, P.q31, v3, o);
+                        c4_partials<0>(o, P, acc);
                     } else {
                         tmem_ld_x16(d1 + 32, ra); tmem_ld_x16(d1 + 48, rb);
                         tmem_ld_x16(d21 + 16, rc);
@@ -395,9 +414,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         requant_store<FAST, 32>(ra, P, P.q1, v1, dst1 + 2 * PLANE);
                         requant_store<FAST, 48>(rb, P, P.q1, v1, dst1 + 3 * PLANE);
                         requant_store<FAST, 96>(rc, P, P.q21, v2, dst2 + 1 * PLANE);
-                        requant_store<FAST, 128>(rd, P, P.q32, v3, dst3 + 1 * PLANE);
-                        requant_store<FAST, 144>(re, P, P.q32, v3, dst3 + 2 * PLANE);
+                        requant<FAST, 128>(rd, P, P.q32, v3, o);
+                        c4_partials<1>(o, P, acc);
+                        requant<FAST, 144>(re, P, P.q32, v3, o);
+                        c4_partials<2>(o, P, acc);
                     }
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) pdst[t * PW] = acc[t];
                 }
                 lap(1);
                 if (i + 1 < niter) {
@@ -496,7 +519,7 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
         s = 2; pl = 2;
         return j == 0;
     };
-    // ---- W31 (rows blk*16 + ch) and W4 (rows blk*8 + 0; rows blk*8 + 1..7 stay zero) ------------------
+    // ---- W31 (rows blk*16 + ch) ----------------------------------------------------------------------
     for (int k = 0; k < 5; ++k)
         for (int bi = 0; bi < 7; ++bi)
             if (S3[bi] >= 0)
@@ -507,8 +530,6 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
                         for (int b = 0; b < 16; ++b) c16[b] = Wt(QV_C3_1, ch, 16 * pl + b, S3[bi], s);
                         put_chunk(img.data() + OFF_W31 + k * T31, NR31, j, bi * 16 + ch, c16);
                     }
-                    for (int b = 0; b < 16; ++b) c16[b] = Wt(QV_C4, 0, 16 * pl + b, S3[bi], s);
-                    put_chunk(img.data() + OFF_W4 + k * T4, NR4, j, bi * 8, c16);
                 }
     // ---- W32 (1x1): K-step 0 = planes 0,1 ; K-step 1 = plane 2 | zero --------------------------------
     for (int ch = 0; ch < 32; ++ch)
@@ -541,6 +562,13 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     addb(QV_C3_1, 112, P.q31); addb(QV_C3_2, 112 + 16, P.q32);
     memcpy(P.bias, bias, sizeof(P.bias));
     P.c4_bias = m.L[QV_C4].b[0]; P.c4_mul = m.L[QV_C4].mul; P.c4_shift = m.L[QV_C4].shift;
+    for (int t = 0; t < 9; ++t)
+        for (int pl = 0; pl < 3; ++pl)
+            for (int j = 0; j < 4; ++j) {
+                unsigned v = 0;
+                for (int b = 0; b < 4; ++b) v |= (unsigned)(uint8_t)Wt(QV_C4, 0, 16 * pl + 4 * j + b, t / 3, t % 3) << (8 * b);
+                P.c4_w[(t * 3 + pl) * 4 + j] = (int)v;
+            }
     cudaError_t e = cudaMalloc(&fm->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fm->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
