@@ -79,6 +79,7 @@ constexpr int SMEM_BYTES = OFF_CTRL + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
 constexpr int NWORKER = 256, NTHREADS = NWORKER + 32;
+constexpr int TR_ITER0 = 300, TR_N = 8;    // profile-mode timeline window
 constexpr int PIPE = 14;                   // pipeline depth in rows: output row y0 appears at iteration 14
 
 // ---- TMEM columns (int32 accumulators) -------------------------------------------------------------
@@ -221,8 +222,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         constexpr uint32_t LP = (uint32_t)(PLANE >> 4) << 16;                  // LBO = one plane: K-halves are planes p, p+1
         constexpr uint32_t LX = 1u << 16;                                      // LBO = 16 B: K-halves are pixels x, x+1 of one plane
         const bool issue = leader && !(P.dbg_flags & 1);
+        long long *stamp = nullptr;                                            // profile mode: clock after every MMA issue
         auto MMA = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
             if (issue) mma_i8_ss(d, HI | a_lo, HI | b_lo, idesc, acc);
+            if (stamp) *stamp++ = clock64();
         };
         const uint32_t sb = sbase >> 4;
         const uint32_t zeroA = sb + (OFF_ZERO >> 4) + ((128u * 16 >> 4) << 16);
@@ -256,6 +259,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 ++ev_work;
                 fence_after_sync();
                 { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
+                const bool tr = P.dbg && leader && unit == 0 && i >= TR_ITER0 && i < TR_ITER0 + TR_N;
+                if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 0] = tc0;
+                stamp = tr ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
                 // ---- C1: a1 row R1 = im2col[par] x W1 (N = 64) --------------------------------------
                 MMA(d1, im, w1, idesc_i8(128, 64), 0);
                 // ---- C2_2 (5x5, 64 -> 16): scatter a1 row R1-2 into the 6-slot ring, N = 96 -----------
@@ -282,6 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 ++ev_mma;
                 __syncwarp();
                 { const long long t = clock64(); t_issue += t - tc0; tc0 = t; }
+                if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 1] = tc0;
             }
         }
         if (P.dbg && leader) { P.dbg[blockIdx.x * 16 + 0] = t_wait; P.dbg[blockIdx.x * 16 + 1] = t_issue; }
@@ -292,7 +299,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         const uint32_t tm_lane = tm + ((uint32_t)(q * 32) << 16);
         uint32_t ev_work = 0, ev_mma = 0;
         long long tw[6] = {0, 0, 0, 0, 0, 0}, tc0 = clock64();
-        auto lap = [&](int k) { const long long t = clock64(); tw[k] += t - tc0; tc0 = t; };
+        int tr_slot = -1;                                         // timeline trace (QV_FUSED_PROFILE): block 0, first unit, a few iterations
+        auto lap = [&](int k) {
+            const long long t = clock64(); tw[k] += t - tc0; tc0 = t;
+            if (tr_slot >= 0 && k < 4) P.dbg[gridDim.x * 16 + tr_slot + k] = t;
+        };
         auto worker_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
@@ -343,6 +354,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
                 const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
+                tr_slot = (P.dbg && unit == 0 && (tid == 0 || tid == 128) && i >= TR_ITER0 && i < TR_ITER0 + TR_N)
+                              ? (i - TR_ITER0) * 16 + 2 + (tid >> 7) * 4 : -1;
                 if (i >= 1 && (P.dbg_flags & 2)) {
                     warp_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1, lane, s_fail);
                     ++ev_mma;
@@ -441,6 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             ++ev_mma;
             fence_after_sync();
             worker_bar();
+            tr_slot = -1;
             lap(5);
         }
         if (P.dbg && (tid == 0 || tid == 128))
@@ -626,14 +640,15 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     const bool prof = getenv("QV_FUSED_PROFILE") != nullptr;
     P.dbg = nullptr;
     P.dbg_flags = getenv("QV_FUSED_EXPERIMENT") ? atoi(getenv("QV_FUSED_EXPERIMENT")) : 0;
-    if (prof && cudaMalloc(&P.dbg, (size_t)grid * 16 * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
-    if (P.dbg) cudaMemsetAsync(P.dbg, 0, (size_t)grid * 16 * sizeof(long long), st);
+    const size_t dbg_n = (size_t)grid * 16 + TR_N * 48;
+    if (prof && cudaMalloc(&P.dbg, dbg_n * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
+    if (P.dbg) cudaMemsetAsync(P.dbg, 0, dbg_n * sizeof(long long), st);
     if (fm->fast) k_fused<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     else k_fused<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     if (launches) *launches += 1;
     cudaError_t e = cudaGetLastError();
     if (P.dbg) {
-        std::vector<long long> h((size_t)grid * 16);
+        std::vector<long long> h(dbg_n);
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), P.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(P.dbg);
@@ -645,6 +660,20 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
                 "worker w4: wait_mma=%.0f drain+epi=%.0f im2col+arrive=%.0f bar=%.0f\n",
                 P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[4] / iters, a[5] / iters,
                 a[8] / iters, a[9] / iters, a[10] / iters, a[11] / iters);
+        // timeline of block 0: per traced iteration, cycles relative to the first issue start
+        const long long *tr = h.data() + (size_t)grid * 16, t0 = tr[0];
+        if (t0)
+            for (int k = 0; k < TR_N; ++k, tr += 16)
+                fprintf(stderr, "[qv fused trace] it %d | mma: start %lld end %lld | w0: commit %lld drained %lld arrived %lld bar %lld | "
+                        "w4: commit %lld drained %lld arrived %lld bar %lld\n", TR_ITER0 + k, tr[0] - t0, tr[1] - t0, tr[2] - t0, tr[3] - t0,
+                        tr[4] - t0, tr[5] - t0, tr[6] - t0, tr[7] - t0, tr[8] - t0, tr[9] - t0);
+        if (t0)
+            for (int k = 0; k < TR_N; ++k) {
+                const long long *sp = h.data() + (size_t)grid * 16 + TR_N * 16 + k * 32, s0 = h[(size_t)grid * 16 + k * 16];
+                fprintf(stderr, "[qv fused stamps] it %d:", TR_ITER0 + k);
+                for (int j = 0; j < 27; ++j) fprintf(stderr, " %lld", sp[j] - (j ? sp[j - 1] : s0));
+                fprintf(stderr, "\n");
+            }
     }
     return e;
 }

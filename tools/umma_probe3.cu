@@ -1,0 +1,247 @@
+// umma_probe3 -- does the tcgen05.mma A-collector (collector::a::fill / use / lastuse) save the
+// shared-memory read of the A operand for kind::i8 SS MMAs, and what are its semantics?
+// Not part of the product; run on the B200 box, results summarised in profiles/.
+//   numerics : MMA1 = A1*B1 (fill) ; MMA2 = "A2"*B2 (lastuse)  -> is D2 = A1*B2 (collector honoured) or A2*B2?
+//   timing   : 32-MMA loops, N = 32..128, all-discard vs (fill,lastuse) pairs vs fill + use chain,
+//              with and without 128 extra threads hammering shared memory (ld.shared) to expose the
+//              smem-bandwidth share the tensor core needs.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../qcnn_gpu_b200/csrc/qv_tcgen05.cuh"
+
+using namespace qv::tc;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+template <int COL>   // 0 discard, 1 fill, 2 use, 3 lastuse
+__device__ __forceinline__ void mma_col(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc)
+{
+    if (COL == 0)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+    if (COL == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+    if (COL == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+    if (COL == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+constexpr int A_BYTES = 2 * 160 * 16;     // [2 K-planes][160 px][16 B]
+constexpr int B_BYTES = 2 * 128 * 16;     // [2 K-chunks][128 rows][16 B]
+
+// out[0]: D after MMA1 (N1 cols at col 0) and MMA2 (N2 cols at col 128)
+// mode: 0 = MMA2 plain (discard) with A2 ; 1 = MMA1 fill, MMA2 lastuse with desc of A2 ; 2 = MMA1 fill, MMA2 lastuse with desc of A1
+//       3 = MMA1 fill, <an unrelated plain MMA with A3 in between>, MMA2 lastuse with desc of A2
+__global__ void k_num(const int8_t *gA, const int8_t *gB, int *out, int mode, int N1, int N2, int *status)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sA = sm, *sB = sm + A_BYTES;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < A_BYTES / 16; i += blockDim.x) reinterpret_cast<int4 *>(sA)[i] = reinterpret_cast<const int4 *>(gA)[i];
+    for (int i = tid; i < B_BYTES / 16; i += blockDim.x) reinterpret_cast<int4 *>(sB)[i] = reinterpret_cast<const int4 *>(gB)[i];
+    fence_proxy_async_smem();
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = s_tmem;
+    if (tid == 0) {
+        const uint64_t a1 = smem_desc(smem_u32(sA), 160 * 16, 128);                 // pixels 0..127
+        const uint64_t a2 = smem_desc(smem_u32(sA) + 9 * 16, 160 * 16, 128);        // pixels 9..136
+        const uint64_t a3 = smem_desc(smem_u32(sA) + 20 * 16, 160 * 16, 128);       // pixels 20..147
+        const uint64_t b1 = smem_desc(smem_u32(sB), 128 * 16, 128);                 // rows 0..N1
+        const uint64_t b2 = smem_desc(smem_u32(sB) + 32 * 16, 128 * 16, 128);       // rows 32..32+N2
+        if (mode == 0) {
+            mma_col<0>(tm, a1, b1, idesc_i8(128, N1), 0);
+            mma_col<0>(tm + 128, a2, b2, idesc_i8(128, N2), 0);
+        } else if (mode == 1) {
+            mma_col<1>(tm, a1, b1, idesc_i8(128, N1), 0);
+            mma_col<3>(tm + 128, a2, b2, idesc_i8(128, N2), 0);
+        } else if (mode == 2) {
+            mma_col<1>(tm, a1, b1, idesc_i8(128, N1), 0);
+            mma_col<3>(tm + 128, a1, b2, idesc_i8(128, N2), 0);
+        } else {
+            mma_col<1>(tm, a1, b1, idesc_i8(128, N1), 0);
+            mma_col<0>(tm + 256, a3, b1, idesc_i8(128, N1), 0);
+            mma_col<3>(tm + 128, a2, b2, idesc_i8(128, N2), 0);
+        }
+        mma_commit(&bar);
+    }
+    const bool ok = mbar_wait(&bar, 0);
+    fence_after_sync();
+    if (!ok) { if (tid == 0) status[0] = 1; }
+    else {
+        for (int j = 0; j < 32; ++j) {
+            uint32_t r[8];
+            tmem_ld_x8(tm + ((uint32_t)(warp * 32) << 16) + j * 8, r);
+            tmem_ld_wait();
+            for (int i = 0; i < 8; ++i) out[(warp * 32 + lane) * 256 + j * 8 + i] = (int)r[i];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+static int run_num()
+{
+    std::vector<int8_t> hA(A_BYTES), hB(B_BYTES);
+    uint32_t s = 4242;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (int8_t)(s >> 24); };
+    for (auto &v : hA) v = rnd();
+    for (auto &v : hB) v = rnd();
+    int8_t *dA, *dB; int *dOut, *dSt;
+    CK(cudaMalloc(&dA, A_BYTES)); CK(cudaMalloc(&dB, B_BYTES)); CK(cudaMalloc(&dOut, 128 * 256 * 4)); CK(cudaMalloc(&dSt, 4));
+    CK(cudaMemcpy(dA, hA.data(), A_BYTES, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), B_BYTES, cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(k_num, cudaFuncAttributeMaxDynamicSharedMemorySize, A_BYTES + B_BYTES));
+    auto ref = [&](int m, int shift, int row0, int n) {
+        long acc = 0;
+        for (int k = 0; k < 32; ++k)
+            acc += (long)hA[(k >> 4) * 160 * 16 + (m + shift) * 16 + (k & 15)] * hB[(k >> 4) * 128 * 16 + (row0 + n) * 16 + (k & 15)];
+        return (int)acc;
+    };
+    const int shapes[][2] = {{96, 96}, {96, 64}, {64, 32}, {32, 32}, {96, 16}};
+    for (auto &sh : shapes)
+        for (int mode = 0; mode < 4; ++mode) {
+            const int N1 = sh[0], N2 = sh[1];
+            CK(cudaMemset(dSt, 0, 4));
+            CK(cudaMemset(dOut, 0xEE, 128 * 256 * 4));
+            k_num<<<1, 128, A_BYTES + B_BYTES>>>(dA, dB, dOut, mode, N1, N2, dSt);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("num mode %d: CUDA error %s\n", mode, cudaGetErrorString(e)); return 2; }
+            int st; std::vector<int> out(128 * 256);
+            CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(out.data(), dOut, out.size() * 4, cudaMemcpyDeviceToHost));
+            long bad1 = 0, eqA1 = 0, eqA2 = 0, eqA3 = 0;
+            for (int m = 0; m < 128; ++m) {
+                for (int n = 0; n < N1; ++n) bad1 += out[m * 256 + n] != ref(m, 0, 0, n);
+                for (int n = 0; n < N2; ++n) {
+                    const int v = out[m * 256 + 128 + n];
+                    eqA1 += v == ref(m, 0, 32, n);
+                    eqA2 += v == ref(m, 9, 32, n);
+                    eqA3 += v == ref(m, 20, 32, n);
+                }
+            }
+            printf("num N1=%3d N2=%3d mode %d (%s): status=%d  D1 mismatches=%ld | D2 == A1*B2: %ld  == A2*B2: %ld  == A3*B2: %ld  of %d\n", N1, N2, mode,
+                   mode == 0 ? "plain, desc A2" : mode == 1 ? "fill A1 ; lastuse, desc A2" : mode == 2 ? "fill A1 ; lastuse, desc A1" : "fill A1 ; plain A3 ; lastuse, desc A2",
+                   st, bad1, eqA1, eqA2, eqA3, 128 * N2);
+        }
+    return 0;
+}
+
+// ---- timing -----------------------------------------------------------------------------------------
+// PAT 0: all discard, every MMA its own A.  PAT 1: pairs (fill A_j, lastuse) with N1 then N2.
+// PAT 2: pairs without collector hints (same A address twice) -- control for "same address" effects.
+// PAT 3: one fill then 31 x use.
+template <int N1, int N2, int PAT>
+__global__ void k_thr(int outer, long long *cycles, int *status, int hammer)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sA = sm;                            // 2 planes x 1024 px x 16 B = 32 KB
+    uint8_t *sB = sm + 32768;                    // 8 KB
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    __shared__ volatile int s_stop;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (32768 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sm)[i] = 0x01010101u * (i & 3);
+    fence_proxy_async_smem();
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); s_stop = 0; }
+    if (warp == 0) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = s_tmem;
+    if (tid == 0) {
+        constexpr uint32_t id1 = idesc_i8(128, N1, 1, 1), id2 = idesc_i8(128, N2, 1, 1);
+        const uint64_t bd1 = smem_desc(smem_u32(sB), 128 * 16, 128), bd2 = smem_desc(smem_u32(sB) + 16 * 16, 128 * 16, 128);
+        const uint64_t ad0 = smem_desc(smem_u32(sA), 16384, 128);
+        long long t0 = clock64();
+        for (int o = 0; o < outer; ++o) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint64_t a = ad0 + (uint64_t)((j * 37) % 800), a2 = ad0 + (uint64_t)((j * 37 + 19) % 800);
+                if (PAT == 0) { mma_col<0>(tm, a, bd1, id1, 1); mma_col<0>(tm + 128, a2, bd2, id2, 1); }
+                if (PAT == 1) { mma_col<1>(tm, a, bd1, id1, 1); mma_col<3>(tm + 128, a, bd2, id2, 1); }
+                if (PAT == 2) { mma_col<0>(tm, a, bd1, id1, 1); mma_col<0>(tm + 128, a, bd2, id2, 1); }
+                if (PAT == 3) {
+                    if (j == 0) mma_col<1>(tm, a, bd1, id1, 1); else mma_col<2>(tm, ad0, bd1, id1, 1);
+                    mma_col<2>(tm + 128, ad0, bd2, id2, 1);
+                }
+            }
+        }
+        long long t1 = clock64();
+        mma_commit(&bar);
+        const bool ok = mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        cycles[0] = t1 - t0;
+        cycles[1] = t2 - t0;
+        status[0] = ok ? 0 : 1;
+        s_stop = 1;
+    } else if (hammer && tid >= 128) {
+        // conflict-free 128-byte ld.shared wavefronts, as fast as 4 warps can issue them
+        const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(sm) + (tid & 31);
+        uint32_t acc = 0;
+        long long n = 0;
+        while (!s_stop) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += p[u * 32];
+            n += 8;
+        }
+        if (acc == 0x12345678u) cycles[7] = acc;
+        if ((tid & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&cycles[2]), (unsigned long long)n);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+template <int N1, int N2, int PAT>
+static void thr_case(long long *dC, int *dSt)
+{
+    static const char *names[] = {"discard, distinct A", "fill/lastuse pairs", "same A twice, no hint", "fill + use chain"};
+    CK(cudaFuncSetAttribute(k_thr<N1, N2, PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8192));
+    const int outer = 64;
+    for (int hammer = 0; hammer < 2; ++hammer) {
+        long long c[4]; int st = 0;
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaMemset(dSt, 0, 4));
+            CK(cudaMemset(dC, 0, 64));
+            k_thr<N1, N2, PAT><<<1, 256, 32768 + 8192>>>(outer, dC, dSt, hammer);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("thr: CUDA error %s\n", cudaGetErrorString(e)); exit(2); }
+        }
+        CK(cudaMemcpy(c, dC, 32, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost));
+        const double per = (double)c[1] / (outer * 16);
+        printf("thr N1=%3d N2=%3d %-24s %s: %.1f cyc per pair (smem wavefronts if A read each time %d, if A reused %d; math %d)  lsu wavefronts/clk %.2f timeout=%d\n",
+               N1, N2, names[PAT], hammer ? "+ld.shared hammer" : "alone            ", per, (128 + N1) / 4 + (128 + N2) / 4, (128 + N1) / 4 + N2 / 4,
+               N1 / 2 + N2 / 2, (double)c[2] / (double)c[1], st);
+    }
+}
+
+int main(int argc, char **argv)
+{
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, 0));
+    printf("# %s  sm_%d%d  %d SMs\n", p.name, p.major, p.minor, p.multiProcessorCount);
+    const char *t = argc > 1 ? argv[1] : "all";
+    if (!strcmp(t, "num") || !strcmp(t, "all"))
+        if (int rc = run_num()) return rc;
+    if (!strcmp(t, "thr") || !strcmp(t, "all")) {
+        long long *dC; int *dSt;
+        CK(cudaMalloc(&dC, 64)); CK(cudaMalloc(&dSt, 4));
+        thr_case<96, 128, 0>(dC, dSt); thr_case<96, 128, 1>(dC, dSt); thr_case<96, 128, 2>(dC, dSt); thr_case<96, 128, 3>(dC, dSt);
+        thr_case<64, 32, 0>(dC, dSt); thr_case<64, 32, 1>(dC, dSt); thr_case<64, 32, 3>(dC, dSt);
+        thr_case<16, 32, 0>(dC, dSt); thr_case<16, 32, 1>(dC, dSt);
+        thr_case<96, 96, 0>(dC, dSt); thr_case<96, 96, 1>(dC, dSt);
+    }
+    return 0;
+}
