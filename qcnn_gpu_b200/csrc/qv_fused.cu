@@ -24,17 +24,28 @@
 // output row completed one step ago sits under the Z block (the MMA adds 0 to it) while the
 // workers drain it; the slot of the row that starts now is zeroed by one small MMA with a zero A.
 //
+// Shared-memory bandwidth is what binds this kernel (ncu: the smem data pipe is ~95 % busy, the tensor
+// core's operand fetches being 70 % of that), and 60 % of the tensor core's traffic is the A operand,
+// re-read by every MMA.  So MMAs that multiply the SAME activation tile are issued back to back and the
+// second takes A from the tensor core's collector (collector::a::fill -> ::lastuse): C2_2 shift s and
+// C2_1 shift s-1 read the same a1 tile, C3_1's centre-tap K-steps and C3_2's two K-steps read the same
+// a2 tiles, and the three ring-slot initialisations share the zero tile.
+//
 // Pipeline.  9 warps: warps 0-7 are workers (TMEM -> requantise -> smem epilogues, im2col for C1,
-// residual + store), warp 8 issues every MMA (one elected lane).  Iteration i, R1 = y0-4+i:
-//   MMA side   : C1 for a1 row R1 (im2col operand); C2_2 scatter of a1 row R1-2; C2_1 scatter of a1
-//                row R1-3; C3_1 scatter of a2 row R1-6; C3_2 of a2 row R1-7; C4 scatter of a3 row R1-9
-//   worker side: drains what iteration i-1 completed: a1 row R1-1, a2 row R1-5, a3 row R1-8, output
-//                row R1-11 (+ residual, clamp, store); im2col for a1 row R1+1.
+// C4 on CUDA cores, residual + store), warp 8 issues every MMA (one elected lane).  Iteration i,
+// R1 = y0-4+i:
+//   MMA side   : C1 for a1 row R1 (im2col operand); C2_2 and C2_1 scatter of a1 row R1-2; C3_1 scatter
+//                and C3_2 of a2 row R1-6
+//   worker side: drains what iteration i-1 completed: a1 row R1-1; a2 row R1-5 plane 2 (C2_2) and a2 row
+//                R1-4 planes 0,1 (C2_1); a3 row R1-8 channels 0-15 (C3_1) and a3 row R1-7 channels 16-47
+//                (C3_2), both only as C4 partial sums; output row R1-10 (+ residual, clamp, store);
+//                im2col for a1 row R1+1.
 // The two sides meet at two pairs of mbarriers per iteration.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -42,6 +53,16 @@
 #include "qv_device.cuh"
 #include "qv_fused.h"
 #include "qv_tcgen05.cuh"
+
+#ifndef QV_C4_LATE
+#define QV_C4_LATE 0
+#endif
+#ifndef QV_BIG_LAST
+#define QV_BIG_LAST 0
+#endif
+#ifndef QV_PRE_WAIT
+#define QV_PRE_WAIT 0
+#endif
 
 namespace qv {
 namespace {
@@ -70,16 +91,18 @@ constexpr int WIMG_BYTES = OFF_BIAS + BIAS_INTS * 4;         // what lives in gl
 constexpr int OFF_A1 = (WIMG_BYTES + 127) / 128 * 128;
 constexpr int OFF_A2 = OFF_A1 + A_SLOTS * A1_ROW;
 constexpr int OFF_IM = OFF_A2 + A_SLOTS * A2_ROW;
-constexpr int OFF_ZERO = OFF_IM + 2 * IM_BYTES;
+constexpr int OFF_ZERO = OFF_IM + 2 * IM_BYTES;   // three im2col stages: stage (i+1)%3 is written while C1 of iteration i-1 may still read (i-1)%3
 constexpr int OFF_IN = OFF_ZERO + ZERO_BYTES;
 constexpr int PART_ROW = 9 * PW * 4;                 // C4 partial dot products of one a3 row: [tap][pixel] int32
-constexpr int OFF_PART = OFF_IN + IN_SLOTS * IN_PITCH;     // [iteration parity][warp half][tap][pixel]
-constexpr int OFF_CTRL = OFF_PART + 2 * 2 * PART_ROW;
+constexpr int OFF_PART0 = OFF_IN + IN_SLOTS * IN_PITCH;    // channels 0-15  (warps 0-3): [iteration & 1][tap][pixel]
+constexpr int OFF_PART1 = OFF_PART0 + 2 * PART_ROW;        // channels 16-47 (warps 4-7): [iteration % 3][tap][pixel], one row ahead
+constexpr int OFF_CTRL = OFF_PART1 + 3 * PART_ROW;
 constexpr int SMEM_BYTES = OFF_CTRL + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
 constexpr int NWORKER = 256, NTHREADS = NWORKER + 32;
 constexpr int TR_ITER0 = 300, TR_N = 8;    // profile-mode timeline window
+constexpr bool C4_LATE = QV_C4_LATE;      // workers: a3 -> C4 after (1) or before (0) the arrive that releases the next MMAs
 constexpr int PIPE = 14;                   // pipeline depth in rows: output row y0 appears at iteration 14
 
 // ---- TMEM columns (int32 accumulators) -------------------------------------------------------------
@@ -172,7 +195,7 @@ __device__ __forceinline__ void c4_partials(const uint32_t (&o)[4], const FusedP
         for (int j = 0; j < 4; ++j) acc[t] = __dp4a((int)o[j], P.c4_w[(t * 3 + PL) * 4 + j], acc[t]);
 }
 
-template <bool FAST>
+template <bool FAST, bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ FusedParams P)
 {
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -213,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         // one elected lane issues the tcgen05 instructions.
         const bool leader = elect_one();
         uint32_t ev_work = 0, ev_mma = 0;
-        long long t_wait = 0, t_issue = 0, tc0 = clock64();
+        long long t_wait = 0, t_issue = 0, tc0 = PROF ? clock64() : 0;
         // Descriptors are handled as their low 32-bit word in 16-byte units: (smem address >> 4) | (LBO >> 4) << 16;
         // the high word (SBO = 128 B, version 1) is a constant.  Everything that changes per iteration is
         // computed up front, so that between two MMAs there is one add per operand: the tensor-pipe queue
@@ -223,10 +246,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         constexpr uint32_t LX = 1u << 16;                                      // LBO = 16 B: K-halves are pixels x, x+1 of one plane
         const bool issue = leader && !(P.dbg_flags & 1);
         long long *stamp = nullptr;                                            // profile mode: clock after every MMA issue
-        auto MMA = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-            if (issue) mma_i8_ss(d, HI | a_lo, HI | b_lo, idesc, acc);
-            if (stamp) *stamp++ = clock64();
+        auto MMA = [&](auto col, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+            if (issue) mma_i8_ss_col<decltype(col)::value>(d, HI | a_lo, HI | b_lo, idesc, acc);
+            if (PROF && stamp) *stamp++ = clock64();
         };
+        constexpr std::integral_constant<int, COL_DISCARD> ONCE{};             // A tile used by this MMA only
+        constexpr std::integral_constant<int, COL_FILL> KEEP{};                // A tile stays in the collector ...
+        constexpr std::integral_constant<int, COL_USE> AGAIN{};                // ... is used from there and kept ...
+        constexpr std::integral_constant<int, COL_LASTUSE> LAST{};             // ... and used from there for the last time
         const uint32_t sb = sbase >> 4;
         const uint32_t zeroA = sb + (OFF_ZERO >> 4) + ((128u * 16 >> 4) << 16);
         const uint32_t anyB = sb + (OFF_W1 >> 4) + (64u << 16);
@@ -237,72 +264,92 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             const int seg = unit % P.nseg;
             const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
-            int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
-            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
+            int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6), i3 = 0;
+            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6), i3 = wrap_inc(i3, 3)) {
                 const int R1p = y0 - 4 + i + 4096;
                 const uint32_t par = i & 1;
                 // ---- everything that depends on the iteration -----------------------------------------
                 const int qa = wrap_sub(c6, 2, 6);                                            // (R1-2) mod 6
-                const uint32_t a1_r2 = sb + (OFF_A1 >> 4) + wrap_sub(c3, 2, 3) * (A1_ROW >> 4) + LP;   // a1 row R1-2 (C2_2)
-                const uint32_t a1_r3 = sb + (OFF_A1 >> 4) + c3 * (A1_ROW >> 4) + LP;                   // a1 row R1-3 (C2_1)
-                const uint32_t a2_r6 = sb + (OFF_A2 >> 4) + c3 * (A2_ROW >> 4);                        // a2 row R1-6 (C3_1)
-                const uint32_t a2_r7 = sb + (OFF_A2 >> 4) + wrap_sub(c3, 7, 3) * (A2_ROW >> 4);        // a2 row R1-7 (C3_2)
+                const uint32_t a1_r2 = sb + (OFF_A1 >> 4) + wrap_sub(c3, 2, 3) * (A1_ROW >> 4) + LP;   // a1 row R1-2 (C2_2, C2_1)
+                const uint32_t a2_r6 = sb + (OFF_A2 >> 4) + c3 * (A2_ROW >> 4);                        // a2 row R1-6 (C3_1, C3_2)
                 const uint32_t b22 = w22 + (qa <= 2 ? 2 - qa : 8 - qa) * 16;         // window start (8 - qa) mod 6 blocks of 16 rows
-                const uint32_t b21 = w21 + ((1 - (R1p - 3)) & 3) * 32;               // (1 - (R1-3) mod 4) mod 4 blocks of 32 rows
+                const uint32_t b21 = w21 + ((1 - (R1p - 2)) & 3) * 32;               // (1 - (R1-2) mod 4) mod 4 blocks of 32 rows
                 const uint32_t b31 = w31 + ((1 - (R1p - 6)) & 3) * 16;
                 const uint32_t d1 = tm + TM_D1 + par * 64, d32 = tm + TM_D32 + par * 32;
                 const uint32_t z22 = tm + TM_R22 + c6 * 16;                          // C2_2 row R1   starts: zero its slot
-                const uint32_t z21 = tm + TM_R21 + ((R1p - 2) & 3) * 32;             // C2_1 row R1-2 starts
+                const uint32_t z21 = tm + TM_R21 + ((R1p - 1) & 3) * 32;             // C2_1 row R1-1 starts
                 const uint32_t z31 = tm + TM_R31 + ((R1p - 5) & 3) * 16;             // C3_1 row R1-5 starts
                 const uint32_t im = sb + ((OFF_IM + par * IM_BYTES) >> 4) + ((128u * 16 >> 4) << 16);
                 warp_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1, lane, s_fail);
                 ++ev_work;
                 fence_after_sync();
-                { const long long t = clock64(); t_wait += t - tc0; tc0 = t; }
-                const bool tr = P.dbg && leader && unit == 0 && i >= TR_ITER0 && i < TR_ITER0 + TR_N;
-                if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 0] = tc0;
-                stamp = tr ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
+                bool tr = false;
+                if (PROF) {
+                    const long long t = clock64(); t_wait += t - tc0; tc0 = t;
+                    tr = P.dbg && leader && unit == 0 && i >= TR_ITER0 && i < TR_ITER0 + TR_N;
+                    if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 0] = tc0;
+                    stamp = tr ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
+                }
                 // ---- C1: a1 row R1 = im2col[par] x W1 (N = 64) --------------------------------------
-                MMA(d1, im, w1, idesc_i8(128, 64), 0);
-                // ---- C2_2 (5x5, 64 -> 16): scatter a1 row R1-2 into the 6-slot ring, N = 96 -----------
-                MMA(z22, zeroA, anyB, idesc_i8(128, 16), 0);
+                MMA(ONCE, d1, im, w1, idesc_i8(128, 64), 0);
+                // ---- the ring slots of the rows that start in this iteration: 0 = zero tile x anything ------
+                MMA(KEEP, z22, zeroA, anyB, idesc_i8(128, 16), 0);
+                MMA(AGAIN, z21, zeroA, anyB, idesc_i8(128, 32), 0);
+                MMA(LAST, z31, zeroA, anyB, idesc_i8(128, 16), 0);
+                auto layer2 = [&]() {
+                // ---- layer 2: scatter a1 row R1-2.  C2_2 (5x5, 64 -> 16) into its 6-slot ring with N = 96, shifts
+                //      s = 0..4 (pixel 4+s) x K-halves h (planes 2h, 2h+1); C2_1 (3x3, 64 -> 32) into its 4-slot
+                //      ring with N = 128 reads the same tile for s = 1..3 and takes it from the collector ------------
 #pragma unroll
-                for (int t = 0; t < 10; ++t)             // t = s*2 + h: shift s = pixel 4+s, K-half h = planes 2h, 2h+1
-                    MMA(tm + TM_R22, a1_r2 + (((t & 1) * 2 * PLANE + (4 + t / 2) * 16) >> 4), b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
-                // ---- C2_1 (3x3, 64 -> 32): scatter a1 row R1-3 into the 4-slot ring, N = 128 -----------
-                MMA(z21, zeroA, anyB, idesc_i8(128, 32), 0);
-#pragma unroll
-                for (int t = 0; t < 6; ++t)
-                    MMA(tm + TM_R21, a1_r3 + (((t & 1) * 2 * PLANE + (5 + t / 2) * 16) >> 4), b21 + t * (T21 >> 4), idesc_i8(128, 128), 1);
-                // ---- C3_1 (3x3, 48 -> 16): scatter a2 row R1-6 into the 4-slot ring, N = 64.  K-steps pair 16-channel
-                //      units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights) ----------------
-                MMA(z31, zeroA, anyB, idesc_i8(128, 16), 0);
-#pragma unroll
-                for (int k = 0; k < 5; ++k)
-                    MMA(tm + TM_R31, k < 3 ? a2_r6 + 6 + k + LP : a2_r6 + ((2 * PLANE) >> 4) + (k == 3 ? 6 : 8) + LX, b31 + k * (T31 >> 4),
-                        idesc_i8(128, 64), 1);
-                // ---- C3_2 (1x1, 48 -> 32) of a2 row R1-7, N = 32 --------------------------------------
-                MMA(d32, a2_r7 + 7 + LP, w32, idesc_i8(128, 32), 0);
-                MMA(d32, a2_r7 + ((2 * PLANE) >> 4) + 7 + LX, w32 + (T32 >> 4), idesc_i8(128, 32), 1);
+                for (int t = 0; t < 10; ++t) {
+                    const int s = t / 2, h = t & 1;
+                    const uint32_t a = a1_r2 + ((h * 2 * PLANE + (4 + s) * 16) >> 4);
+                    if (s >= 1 && s <= 3) {
+                        MMA(KEEP, tm + TM_R22, a, b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
+                        MMA(LAST, tm + TM_R21, a, b21 + ((s - 1) * 2 + h) * (T21 >> 4), idesc_i8(128, 128), 1);
+                    } else {
+                        MMA(ONCE, tm + TM_R22, a, b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
+                    }
+                }
+                };
+                if (!QV_BIG_LAST) layer2();
+                // ---- layer 3 on a2 row R1-6.  C3_1 (3x3, 48 -> 16) scatters into its 4-slot ring, N = 64; its K-steps
+                //      pair 16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights).
+                //      C3_2 (1x1, 48 -> 32, N = 32) needs exactly the tiles of K-steps 1 and 3 (centre pixel: planes 0,1
+                //      and zero weights | plane 2) and takes them from the collector -------------------------------------
+                MMA(ONCE, tm + TM_R31, a2_r6 + 6 + LP, b31, idesc_i8(128, 64), 1);
+                MMA(KEEP, tm + TM_R31, a2_r6 + 7 + LP, b31 + (T31 >> 4), idesc_i8(128, 64), 1);
+                MMA(LAST, d32, a2_r6 + 7 + LP, w32, idesc_i8(128, 32), 0);
+                MMA(ONCE, tm + TM_R31, a2_r6 + 8 + LP, b31 + 2 * (T31 >> 4), idesc_i8(128, 64), 1);
+                MMA(KEEP, tm + TM_R31, a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, b31 + 3 * (T31 >> 4), idesc_i8(128, 64), 1);
+                MMA(LAST, d32, a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, w32 + (T32 >> 4), idesc_i8(128, 32), 1);
+                MMA(ONCE, tm + TM_R31, a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, b31 + 4 * (T31 >> 4), idesc_i8(128, 64), 1);
+                // the wide layer-2 MMAs go last: they execute slower than they issue, so the tensor pipe still has a
+                // backlog to work on while this warp goes through the handshake below
+                if (QV_BIG_LAST) layer2();
                 if (leader) mma_commit(&bar_mma[ev_mma & 1]);
                 ++ev_mma;
                 __syncwarp();
-                { const long long t = clock64(); t_issue += t - tc0; tc0 = t; }
-                if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 1] = tc0;
+                if (PROF) {
+                    const long long t = clock64(); t_issue += t - tc0; tc0 = t;
+                    if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 1] = tc0;
+                }
             }
         }
-        if (P.dbg && leader) { P.dbg[blockIdx.x * 16 + 0] = t_wait; P.dbg[blockIdx.x * 16 + 1] = t_issue; }
+        if (PROF && P.dbg && leader) { P.dbg[blockIdx.x * 16 + 0] = t_wait; P.dbg[blockIdx.x * 16 + 1] = t_issue; }
     } else {
         // ================================= workers =========================================
         const int q = warp & 3, hh = warp >> 2;
         const int m = q * 32 + lane;                              // this thread's MMA row / pixel
         const uint32_t tm_lane = tm + ((uint32_t)(q * 32) << 16);
         uint32_t ev_work = 0, ev_mma = 0;
-        long long tw[6] = {0, 0, 0, 0, 0, 0}, tc0 = clock64();
+        long long tw[6] = {0, 0, 0, 0, 0, 0}, tc0 = PROF ? clock64() : 0, t_ldtm = 0;
         int tr_slot = -1;                                         // timeline trace (QV_FUSED_PROFILE): block 0, first unit, a few iterations
         auto lap = [&](int k) {
-            const long long t = clock64(); tw[k] += t - tc0; tc0 = t;
-            if (tr_slot >= 0 && k < 4) P.dbg[gridDim.x * 16 + tr_slot + k] = t;
+            if (PROF) {
+                const long long t = clock64(); tw[k] += t - tc0; tc0 = t;
+                if (tr_slot >= 0 && k < 4) P.dbg[gridDim.x * 16 + tr_slot + k] = t;
+            }
         };
         auto worker_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
@@ -350,12 +397,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 ++ev_work;
             }
             int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
+            int i3 = 0;                                           // i mod 3: stage of the channels-16-47 partial-sum buffer
             int c4_s1 = 0, c4_s2 = 0;
-            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
+            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6), i3 = wrap_inc(i3, 3)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
                 const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
-                tr_slot = (P.dbg && unit == 0 && (tid == 0 || tid == 128) && i >= TR_ITER0 && i < TR_ITER0 + TR_N)
-                              ? (i - TR_ITER0) * 16 + 2 + (tid >> 7) * 4 : -1;
+                if (PROF)
+                    tr_slot = (P.dbg && unit == 0 && (tid == 0 || tid == 128) && i >= TR_ITER0 && i < TR_ITER0 + TR_N)
+                                  ? (i - TR_ITER0) * 16 + 2 + (tid >> 7) * 4 : -1;
                 if (i >= 1 && (P.dbg_flags & 2)) {
                     warp_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1, lane, s_fail);
                     ++ev_mma;
@@ -367,79 +416,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     fence_after_sync();
                     lap(0);
                     const uint32_t par = (i - 1) & 1;
-                    // ---- (A) output row R1-10: C4 = the nine-tap sum of the per-pixel partial dot products that both
-                    //      warp halves left in smem for a3 row R1-9 one iteration ago, accumulated over three rows in
-                    //      two registers (s1: row above started, s2: row above + this row), then applyRes_y.
                     if (hh == 0 && i >= 2) {
-                        const int *part = reinterpret_cast<const int *>(sm + OFF_PART + ((i - 1) & 1) * 2 * PART_ROW) + 8 + m;
+                        const int *part0 = reinterpret_cast<const int *>(sm + OFF_PART0 + ((i - 1) & 1) * PART_ROW) + 8 + m;
+                        const int *part1 = reinterpret_cast<const int *>(sm + OFF_PART1 + wrap_sub(i3, 2, 3) * PART_ROW) + 8 + m;
                         int q[3];
 #pragma unroll
                         for (int r = 0; r < 3; ++r) {
                             int v = 0;
 #pragma unroll
                             for (int sft = 0; sft < 3; ++sft)
-                                v += part[(r * 3 + sft) * PW + sft - 1] + part[(9 + r * 3 + sft) * PW + sft - 1];
+                                v += part0[(r * 3 + sft) * PW + sft - 1] + part1[(r * 3 + sft) * PW + sft - 1];
                             q[r] = v;
                         }
-                        const int u4 = c4_s2 + q[2];              // out row y: a3 rows y-1 (tap row 0), y (1), y+1 (2)
+                        const int u4 = c4_s2 + q[2];
                         c4_s2 = c4_s1 + q[1];
                         c4_s1 = q[0];
                         const int rowo = R1 - 10;
                         if (rowo >= y0 && rowo < y1 && m < WT && X0 + m < W) {
                             const int x = sm[OFF_IN + ((R1p - 10) & (IN_SLOTS - 1)) * IN_PITCH + 8 + m];
-                            outf[(size_t)rowo * W + X0 + m] = (uint8_t)residual_apply(u4 + P.c4_bias, x, P.c4_mul, P.c4_shift);   // cnn.cu:507-523
+                            outf[(size_t)rowo * W + X0 + m] = (uint8_t)residual_apply(u4 + P.c4_bias, x, P.c4_mul, P.c4_shift);
                         }
                     }
-                    // ---- (B) drain what iteration i-1 completed.  Ten 16-column groups, five per warp half:
-                    //      a1 row R1-1 : D1[par] groups 0..3                      -> a1 planes 0..3
-                    //      a2 row R1-5 : C2_2 ring slot (16) -> plane 2 ; C2_1 ring slot (32) -> planes 0,1
-                    //      a3 row R1-8 : C3_1 ring slot (16) = channels 0..15 ; C3_2 D32[par] (32) = channels 16..47.
-                    //      a3 is never stored: its only consumer, C4 (48 -> 1), is nine dp4a partial sums per pixel and
-                    //      16 channels taken straight from the requantised registers.
-                    const int row1 = R1 - 1, row2 = R1 - 5, row3 = R1 - 8;
-                    const bool v1 = row1 >= 0 && row1 < H && X0 - 4 + m >= 0 && X0 - 4 + m < W;
-                    const bool v2 = row2 >= 0 && row2 < H && X0 - 2 + m >= 0 && X0 - 2 + m < W;
-                    const bool v3 = row3 >= 0 && row3 < H && X0 - 1 + m >= 0 && X0 - 1 + m < W;
+                    const bool xa1 = X0 - 4 + m >= 0 && X0 - 4 + m < W, xa2 = X0 - 2 + m >= 0 && X0 - 2 + m < W, xa3 = X0 - 1 + m >= 0 && X0 - 1 + m < W;
+                    const bool v1 = R1 - 1 >= 0 && R1 - 1 < H && xa1;
                     uint8_t *dst1 = sm + OFF_A1 + wrap_sub(c3, 1, 3) * A1_ROW + (4 + m) * 16;
-                    uint8_t *dst2 = sm + OFF_A2 + wrap_sub(c3, 5, 3) * A2_ROW + (6 + m) * 16;
-                    int *pdst = reinterpret_cast<int *>(sm + OFF_PART + (i & 1) * 2 * PART_ROW + hh * PART_ROW) + 7 + m;
                     const uint32_t d1 = tm_lane + TM_D1 + par * 64;
-                    const uint32_t d22 = tm_lane + TM_R22 + wrap_sub(c6, 5, 6) * 16, d21 = tm_lane + TM_R21 + ((R1p - 5) & 3) * 32;
-                    const uint32_t d31 = tm_lane + TM_R31 + ((R1p - 8) & 3) * 16, d32 = tm_lane + TM_D32 + par * 32;
                     uint32_t ra[16], rb[16], rc[16], rd[16], re[16], o[4];
                     int acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                     if (hh == 0) {
+                        const bool v2 = R1 - 5 >= 0 && R1 - 5 < H && xa2, v2n = R1 - 4 >= 0 && R1 - 4 < H && xa2;
+                        const bool v3 = R1 - 8 >= 0 && R1 - 8 < H && xa3;
+                        uint8_t *dst2 = sm + OFF_A2 + wrap_sub(c3, 5, 3) * A2_ROW + (6 + m) * 16;
+                        uint8_t *dst2n = sm + OFF_A2 + wrap_sub(c3, 4, 3) * A2_ROW + (6 + m) * 16;
                         tmem_ld_x16(d1 + 0, ra); tmem_ld_x16(d1 + 16, rb);
-                        tmem_ld_x16(d22, rc); tmem_ld_x16(d21, rd);
-                        tmem_ld_x16(d31, re);
+                        tmem_ld_x16(tm_lane + TM_R22 + wrap_sub(c6, 5, 6) * 16, rc);
+                        tmem_ld_x16(tm_lane + TM_R21 + ((R1p - 4) & 3) * 32, rd);
+                        tmem_ld_x16(tm_lane + TM_R31 + ((R1p - 8) & 3) * 16, re);
                         tmem_ld_wait();
                         requant_store<FAST, 0>(ra, P, P.q1, v1, dst1 + 0 * PLANE);
                         requant_store<FAST, 16>(rb, P, P.q1, v1, dst1 + 1 * PLANE);
                         requant_store<FAST, 64>(rc, P, P.q22, v2, dst2 + 2 * PLANE);
-                        requant_store<FAST, 80>(rd, P, P.q21, v2, dst2 + 0 * PLANE);
+                        requant_store<FAST, 80>(rd, P, P.q21, v2n, dst2n + 0 * PLANE);
                         requant<FAST, 112>(re, P, P.q31, v3, o);
                         c4_partials<0>(o, P, acc);
                     } else {
+                        const bool v2n = R1 - 4 >= 0 && R1 - 4 < H && xa2;
+                        const bool v3n = R1 - 7 >= 0 && R1 - 7 < H && xa3;
+                        uint8_t *dst2n = sm + OFF_A2 + wrap_sub(c3, 4, 3) * A2_ROW + (6 + m) * 16;
+                        const uint32_t d32 = tm_lane + TM_D32 + par * 32;
                         tmem_ld_x16(d1 + 32, ra); tmem_ld_x16(d1 + 48, rb);
-                        tmem_ld_x16(d21 + 16, rc);
+                        tmem_ld_x16(tm_lane + TM_R21 + ((R1p - 4) & 3) * 32 + 16, rc);
                         tmem_ld_x16(d32 + 0, rd); tmem_ld_x16(d32 + 16, re);
                         tmem_ld_wait();
                         requant_store<FAST, 32>(ra, P, P.q1, v1, dst1 + 2 * PLANE);
                         requant_store<FAST, 48>(rb, P, P.q1, v1, dst1 + 3 * PLANE);
-                        requant_store<FAST, 96>(rc, P, P.q21, v2, dst2 + 1 * PLANE);
-                        requant<FAST, 128>(rd, P, P.q32, v3, o);
+                        requant_store<FAST, 96>(rc, P, P.q21, v2n, dst2n + 1 * PLANE);
+                        requant<FAST, 128>(rd, P, P.q32, v3n, o);
                         c4_partials<1>(o, P, acc);
-                        requant<FAST, 144>(re, P, P.q32, v3, o);
+                        requant<FAST, 144>(re, P, P.q32, v3n, o);
                         c4_partials<2>(o, P, acc);
                     }
+                    int *pdst = reinterpret_cast<int *>(sm + (hh == 0 ? OFF_PART0 + (i & 1) * PART_ROW : OFF_PART1 + i3 * PART_ROW)) + 7 + m;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) pdst[t * PW] = acc[t];
                 }
                 lap(1);
                 if (i + 1 < niter) {
                     if (hh == 1) im2col(R1 + 1, (i + 1) & 1);
-                    fence_proxy_async_smem();                     // st.shared above -> visible to the tensor core
-                    fence_before_sync();                          // tcgen05.ld above ordered before the MMAs that overwrite D
+                    fence_proxy_async_smem();
+                    fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
                     ++ev_work;
@@ -457,8 +502,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             tr_slot = -1;
             lap(5);
         }
-        if (P.dbg && (tid == 0 || tid == 128))
+        if (PROF && P.dbg && (tid == 0 || tid == 128))
+        {
             for (int k = 0; k < 6; ++k) P.dbg[blockIdx.x * 16 + 2 + (tid >> 7) * 6 + k] = tw[k];
+            P.dbg[blockIdx.x * 16 + 14 + (tid >> 7)] = t_ldtm;
+        }
     }
     fence_before_sync();
     __syncthreads();
@@ -545,11 +593,12 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
                         put_chunk(img.data() + OFF_W31 + k * T31, NR31, j, bi * 16 + ch, c16);
                     }
                 }
-    // ---- W32 (1x1): K-step 0 = planes 0,1 ; K-step 1 = plane 2 | zero --------------------------------
+    // ---- W32 (1x1): K-step 0 = planes 0,1 of the centre pixel (the tile of C3_1's K-step 1) ; K-step 1 = zero | plane 2
+    //      (the tile of C3_1's K-step 3: plane 2 of the pixel to the left | plane 2 of the centre pixel) ------------------
     for (int ch = 0; ch < 32; ++ch)
         for (int pl = 0; pl < 3; ++pl) {
             for (int b = 0; b < 16; ++b) c16[b] = Wt(QV_C3_2, ch, 16 * pl + b, 0, 0);
-            put_chunk(img.data() + OFF_W32 + (pl / 2) * T32, NR32, pl % 2, ch, c16);
+            put_chunk(img.data() + OFF_W32 + (pl / 2) * T32, NR32, pl == 2 ? 1 : pl, ch, c16);
         }
     // ---- requantiser constants ---------------------------------------------------------------------
     FusedModel *fm = new FusedModel();
@@ -586,8 +635,9 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     cudaError_t e = cudaMalloc(&fm->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fm->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     int dev = 0, sms = 148;
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -643,8 +693,9 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     const size_t dbg_n = (size_t)grid * 16 + TR_N * 48;
     if (prof && cudaMalloc(&P.dbg, dbg_n * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
     if (P.dbg) cudaMemsetAsync(P.dbg, 0, dbg_n * sizeof(long long), st);
-    if (fm->fast) k_fused<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
-    else k_fused<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    if (fm->fast && P.dbg) k_fused<true, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    else if (fm->fast) k_fused<true, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    else k_fused<false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     if (launches) *launches += 1;
     cudaError_t e = cudaGetLastError();
     if (P.dbg) {
@@ -652,14 +703,14 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), P.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(P.dbg);
-        double a[14] = {0};
-        for (int b = 0; b < grid; ++b) for (int k = 0; k < 14; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
+        double a[16] = {0};
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
         const double iters = (double)P.n_units / grid * (P.seg_rows + PIPE);
         fprintf(stderr, "[qv fused profile] units=%d grid=%d iters/block~%.0f | cycles per iteration: MMA warp wait=%.0f issue=%.0f | "
-                "worker w0: wait_mma=%.0f drain+epi=%.0f im2col+arrive=%.0f bar=%.0f | "
-                "worker w4: wait_mma=%.0f drain+epi=%.0f im2col+arrive=%.0f bar=%.0f\n",
-                P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[4] / iters, a[5] / iters,
-                a[8] / iters, a[9] / iters, a[10] / iters, a[11] / iters);
+                "worker w0: wait_mma=%.0f drain(a1,a2)=%.0f (of which tcgen05.ld+wait %.0f) im2col+arrive=%.0f a3+c4=%.0f bar=%.0f | "
+                "worker w4: wait_mma=%.0f drain(a1,a2)=%.0f (tcgen05.ld+wait %.0f) im2col+arrive=%.0f a3+c4=%.0f bar=%.0f\n",
+                P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[14] / iters, a[4] / iters, a[6] / iters, a[5] / iters,
+                a[8] / iters, a[9] / iters, a[15] / iters, a[10] / iters, a[12] / iters, a[11] / iters);
         // timeline of block 0: per traced iteration, cycles relative to the first issue start
         const long long *tr = h.data() + (size_t)grid * 16, t0 = tr[0];
         if (t0)

@@ -99,6 +99,28 @@ __device__ __forceinline__ void mma_i8_ss(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, with an A-collector hint (measured: tools/umma_probe3.cu, profiles/r1_probe3_collector.log).  FILL keeps
+// the A tile in the tensor core's collector after use; USE / LASTUSE take A from the collector instead of
+// reading shared memory again (the descriptor must still name the same tile: if the collector was
+// invalidated by an intervening MMA, the hardware re-reads it from there).
+enum Collector { COL_DISCARD = 0, COL_FILL = 1, COL_USE = 2, COL_LASTUSE = 3 };
+template <int COL>
+__device__ __forceinline__ void mma_i8_ss_col(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    if (COL == COL_DISCARD) mma_i8_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+    if (COL == COL_FILL)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    if (COL == COL_USE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    if (COL == COL_LASTUSE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // A operand from TMEM (128 lanes x K/4 columns).
 __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
