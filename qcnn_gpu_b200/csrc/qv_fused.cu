@@ -64,9 +64,14 @@
 #define QV_PRE_WAIT 0
 #endif
 
+#ifndef QV_EXP
+#define QV_EXP 0
+#endif
+
 namespace qv {
 namespace {
 using namespace tc;
+constexpr int EXP = QV_EXP;   // timing experiments only (tools/build_variants.sh): 1 no C4 on the workers, 2 no requantiser arithmetic, 4 no im2col
 
 constexpr int WT = 120;                    // output columns per strip
 constexpr int PW = 136;                    // pixel pitch of every activation row buffer
@@ -129,16 +134,26 @@ struct FusedParams {
     int c4_bias, c4_mul, c4_shift;
     int c4_w[108];                     // C4 weights [tap][plane][4 words], 4 channels per word (CUDA-core dp4a)
     long long *dbg;                    // optional per-block phase timers (QV_FUSED_PROFILE=1), else null
+    uint32_t sbase16, tmem_base;       // what c_mma was built for (checked by the kernel)
     int dbg_flags;                     // tuning experiments only (QV_FUSED_EXPERIMENT): 1 = issue no MMAs, 2 = workers skip the drains
     int bias[BIAS_INTS];               // per accumulator column: layer bias (+ rounding bias on the FAST path)
 };
 
-__device__ __forceinline__ int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+// Operand addresses of the 27 MMAs of one row iteration, for each of the 12 phases R1 mod 12 (the ring rotations have
+// periods 2, 3, 4 and 6).  Lives in constant memory so that the MMA warp forms its descriptors with uniform-datapath
+// loads only: measured (profiles/r1_probe3_contention*.log), integer ALU work of the worker warps that share the MMA
+// warp's SM sub-partition starves exactly the ALU-pipe instructions (address arithmetic, R2UR) an issue loop would
+// otherwise need, and the tensor pipe's queue is only a handful of instructions deep.
+struct MmaEntry { uint32_t a_lo, b_lo, d, pad; };       // low descriptor words (16-byte units | LBO << 16), TMEM address
+constexpr int N_MMA = 27, N_PHASE = 12;
+__constant__ MmaEntry c_mma[N_PHASE][N_MMA + 1];
+
+__host__ __device__ __forceinline__ int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
 // Ring indices without divisions: c3 / c6 track R1 mod 3 / mod 6 incrementally; (c - k) mod n for a
 // compile-time k is one compare-and-add.  Powers of two use masks on R1 + 4096 (R1 may be negative).
-__device__ __forceinline__ int wrap_sub(int c, int k, int n) { const int v = c - (k % n); return v < 0 ? v + n : v; }
-__device__ __forceinline__ int wrap_inc(int c, int n) { return c + 1 == n ? 0 : c + 1; }
+__host__ __device__ __forceinline__ int wrap_sub(int c, int k, int n) { const int v = c - (k % n); return v < 0 ? v + n : v; }
+__host__ __device__ __forceinline__ int wrap_inc(int c, int n) { return c + 1 == n ? 0 : c + 1; }
 
 // One lane polls the mbarrier (every try_wait is a shared-memory access that competes with the tensor
 // core's operand fetches: 256 pollers measurably slow the MMAs down), the rest of the warp parks at
@@ -182,7 +197,8 @@ __device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const Fus
                                               uint8_t *dst)
 {
     uint32_t o[4];
-    requant<FAST, BOFF>(r, P, g, valid, o);
+    if (EXP & 2) { o[0] = r[0] & 0x7f7f7f7fu; o[1] = r[5] & 0x7f7f7f7fu; o[2] = r[10] & 0x7f7f7f7fu; o[3] = r[15] & 0x7f7f7f7fu; }
+    else requant<FAST, BOFF>(r, P, g, valid, o);
     *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 // C4 (48 -> 1, 3x3) partial dot products of one pixel's 16 a3 channels (plane PL) with all nine taps
@@ -242,8 +258,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         // computed up front, so that between two MMAs there is one add per operand: the tensor-pipe queue
         // is short, and a long scalar stretch in this warp drains it.
         constexpr uint64_t HI = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
-        constexpr uint32_t LP = (uint32_t)(PLANE >> 4) << 16;                  // LBO = one plane: K-halves are planes p, p+1
-        constexpr uint32_t LX = 1u << 16;                                      // LBO = 16 B: K-halves are pixels x, x+1 of one plane
         const bool issue = leader && !(P.dbg_flags & 1);
         long long *stamp = nullptr;                                            // profile mode: clock after every MMA issue
         auto MMA = [&](auto col, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
@@ -254,32 +268,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         constexpr std::integral_constant<int, COL_FILL> KEEP{};                // A tile stays in the collector ...
         constexpr std::integral_constant<int, COL_USE> AGAIN{};                // ... is used from there and kept ...
         constexpr std::integral_constant<int, COL_LASTUSE> LAST{};             // ... and used from there for the last time
-        const uint32_t sb = sbase >> 4;
-        const uint32_t zeroA = sb + (OFF_ZERO >> 4) + ((128u * 16 >> 4) << 16);
-        const uint32_t anyB = sb + (OFF_W1 >> 4) + (64u << 16);
-        const uint32_t w1 = sb + (OFF_W1 >> 4) + (64u << 16);
-        const uint32_t w22 = sb + (OFF_W22 >> 4) + ((uint32_t)NR22 << 16), w21 = sb + (OFF_W21 >> 4) + ((uint32_t)NR21 << 16);
-        const uint32_t w31 = sb + (OFF_W31 >> 4) + ((uint32_t)NR31 << 16), w32 = sb + (OFF_W32 >> 4) + ((uint32_t)NR32 << 16);
+        if ((sbase >> 4) != P.sbase16 || tm != P.tmem_base) { if (lane == 0) *s_fail = 2; }     // c_mma does not describe this CTA
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg;
             const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
-            int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6), i3 = 0;
-            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6), i3 = wrap_inc(i3, 3)) {
-                const int R1p = y0 - 4 + i + 4096;
-                const uint32_t par = i & 1;
-                // ---- everything that depends on the iteration -----------------------------------------
-                const int qa = wrap_sub(c6, 2, 6);                                            // (R1-2) mod 6
-                const uint32_t a1_r2 = sb + (OFF_A1 >> 4) + wrap_sub(c3, 2, 3) * (A1_ROW >> 4) + LP;   // a1 row R1-2 (C2_2, C2_1)
-                const uint32_t a2_r6 = sb + (OFF_A2 >> 4) + c3 * (A2_ROW >> 4);                        // a2 row R1-6 (C3_1, C3_2)
-                const uint32_t b22 = w22 + (qa <= 2 ? 2 - qa : 8 - qa) * 16;         // window start (8 - qa) mod 6 blocks of 16 rows
-                const uint32_t b21 = w21 + ((1 - (R1p - 2)) & 3) * 32;               // (1 - (R1-2) mod 4) mod 4 blocks of 32 rows
-                const uint32_t b31 = w31 + ((1 - (R1p - 6)) & 3) * 16;
-                const uint32_t d1 = tm + TM_D1 + par * 64, d32 = tm + TM_D32 + par * 32;
-                const uint32_t z22 = tm + TM_R22 + c6 * 16;                          // C2_2 row R1   starts: zero its slot
-                const uint32_t z21 = tm + TM_R21 + ((R1p - 1) & 3) * 32;             // C2_1 row R1-1 starts
-                const uint32_t z31 = tm + TM_R31 + ((R1p - 5) & 3) * 16;             // C3_1 row R1-5 starts
-                const uint32_t im = sb + ((OFF_IM + par * IM_BYTES) >> 4) + ((128u * 16 >> 4) << 16);
+            int ph = mod_pos(y0 - 4, N_PHASE);
+            for (int i = 0; i < niter; ++i, ph = wrap_inc(ph, N_PHASE)) {
+                const MmaEntry *tab = c_mma[ph];
                 warp_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1, lane, s_fail);
                 ++ev_work;
                 fence_after_sync();
@@ -290,43 +286,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 0] = tc0;
                     stamp = tr ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
                 }
-                // ---- C1: a1 row R1 = im2col[par] x W1 (N = 64) --------------------------------------
-                MMA(ONCE, d1, im, w1, idesc_i8(128, 64), 0);
+                int k = 0;
+                auto T = [&](auto col, uint32_t idesc, uint32_t acc) { MMA(col, tab[k].d, tab[k].a_lo, tab[k].b_lo, idesc, acc); ++k; };
+                // ---- C1: a1 row R1 = im2col[R1 & 1] x W1 (N = 64) --------------------------------------
+                T(ONCE, idesc_i8(128, 64), 0);
                 // ---- the ring slots of the rows that start in this iteration: 0 = zero tile x anything ------
-                MMA(KEEP, z22, zeroA, anyB, idesc_i8(128, 16), 0);
-                MMA(AGAIN, z21, zeroA, anyB, idesc_i8(128, 32), 0);
-                MMA(LAST, z31, zeroA, anyB, idesc_i8(128, 16), 0);
-                auto layer2 = [&]() {
+                T(KEEP, idesc_i8(128, 16), 0);        // C2_2 row R1
+                T(AGAIN, idesc_i8(128, 32), 0);       // C2_1 row R1-1
+                T(LAST, idesc_i8(128, 16), 0);        // C3_1 row R1-5
                 // ---- layer 2: scatter a1 row R1-2.  C2_2 (5x5, 64 -> 16) into its 6-slot ring with N = 96, shifts
                 //      s = 0..4 (pixel 4+s) x K-halves h (planes 2h, 2h+1); C2_1 (3x3, 64 -> 32) into its 4-slot
                 //      ring with N = 128 reads the same tile for s = 1..3 and takes it from the collector ------------
 #pragma unroll
                 for (int t = 0; t < 10; ++t) {
-                    const int s = t / 2, h = t & 1;
-                    const uint32_t a = a1_r2 + ((h * 2 * PLANE + (4 + s) * 16) >> 4);
+                    const int s = t / 2;
                     if (s >= 1 && s <= 3) {
-                        MMA(KEEP, tm + TM_R22, a, b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
-                        MMA(LAST, tm + TM_R21, a, b21 + ((s - 1) * 2 + h) * (T21 >> 4), idesc_i8(128, 128), 1);
+                        T(KEEP, idesc_i8(128, 96), 1);
+                        T(LAST, idesc_i8(128, 128), 1);
                     } else {
-                        MMA(ONCE, tm + TM_R22, a, b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
+                        T(ONCE, idesc_i8(128, 96), 1);
                     }
                 }
-                };
-                if (!QV_BIG_LAST) layer2();
                 // ---- layer 3 on a2 row R1-6.  C3_1 (3x3, 48 -> 16) scatters into its 4-slot ring, N = 64; its K-steps
                 //      pair 16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights).
                 //      C3_2 (1x1, 48 -> 32, N = 32) needs exactly the tiles of K-steps 1 and 3 (centre pixel: planes 0,1
                 //      and zero weights | plane 2) and takes them from the collector -------------------------------------
-                MMA(ONCE, tm + TM_R31, a2_r6 + 6 + LP, b31, idesc_i8(128, 64), 1);
-                MMA(KEEP, tm + TM_R31, a2_r6 + 7 + LP, b31 + (T31 >> 4), idesc_i8(128, 64), 1);
-                MMA(LAST, d32, a2_r6 + 7 + LP, w32, idesc_i8(128, 32), 0);
-                MMA(ONCE, tm + TM_R31, a2_r6 + 8 + LP, b31 + 2 * (T31 >> 4), idesc_i8(128, 64), 1);
-                MMA(KEEP, tm + TM_R31, a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, b31 + 3 * (T31 >> 4), idesc_i8(128, 64), 1);
-                MMA(LAST, d32, a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, w32 + (T32 >> 4), idesc_i8(128, 32), 1);
-                MMA(ONCE, tm + TM_R31, a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, b31 + 4 * (T31 >> 4), idesc_i8(128, 64), 1);
-                // the wide layer-2 MMAs go last: they execute slower than they issue, so the tensor pipe still has a
-                // backlog to work on while this warp goes through the handshake below
-                if (QV_BIG_LAST) layer2();
+                T(ONCE, idesc_i8(128, 64), 1);
+                T(KEEP, idesc_i8(128, 64), 1);
+                T(LAST, idesc_i8(128, 32), 0);
+                T(ONCE, idesc_i8(128, 64), 1);
+                T(KEEP, idesc_i8(128, 64), 1);
+                T(LAST, idesc_i8(128, 32), 1);
+                T(ONCE, idesc_i8(128, 64), 1);
                 if (leader) mma_commit(&bar_mma[ev_mma & 1]);
                 ++ev_mma;
                 __syncwarp();
@@ -390,7 +381,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 const int R1 = y0 - 4;
                 for (int r = R1 - 2; r <= R1 + 3; ++r) store_in(r, load_in(r));
                 worker_bar();
-                if (hh == 1) im2col(R1, 0);
+                if (hh == 1) im2col(R1, R1 & 1);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
@@ -415,8 +406,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     ++ev_mma;
                     fence_after_sync();
                     lap(0);
-                    const uint32_t par = (i - 1) & 1;
-                    if (hh == 0 && i >= 2) {
+                    const uint32_t par = (R1p - 1) & 1;         // D1 / D32 stage the MMAs of iteration i-1 wrote
+                    if (!(EXP & 1) && hh == 0 && i >= 2) {
                         const int *part0 = reinterpret_cast<const int *>(sm + OFF_PART0 + ((i - 1) & 1) * PART_ROW) + 8 + m;
                         const int *part1 = reinterpret_cast<const int *>(sm + OFF_PART1 + wrap_sub(i3, 2, 3) * PART_ROW) + 8 + m;
                         int q[3];
@@ -457,8 +448,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         requant_store<FAST, 16>(rb, P, P.q1, v1, dst1 + 1 * PLANE);
                         requant_store<FAST, 64>(rc, P, P.q22, v2, dst2 + 2 * PLANE);
                         requant_store<FAST, 80>(rd, P, P.q21, v2n, dst2n + 0 * PLANE);
+                        if (!(EXP & 1)) {
                         requant<FAST, 112>(re, P, P.q31, v3, o);
                         c4_partials<0>(o, P, acc);
+                        }
                     } else {
                         const bool v2n = R1 - 4 >= 0 && R1 - 4 < H && xa2;
                         const bool v3n = R1 - 7 >= 0 && R1 - 7 < H && xa3;
@@ -471,18 +464,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         requant_store<FAST, 32>(ra, P, P.q1, v1, dst1 + 2 * PLANE);
                         requant_store<FAST, 48>(rb, P, P.q1, v1, dst1 + 3 * PLANE);
                         requant_store<FAST, 96>(rc, P, P.q21, v2n, dst2n + 1 * PLANE);
+                        if (!(EXP & 1)) {
                         requant<FAST, 128>(rd, P, P.q32, v3n, o);
                         c4_partials<1>(o, P, acc);
                         requant<FAST, 144>(re, P, P.q32, v3n, o);
                         c4_partials<2>(o, P, acc);
+                        }
                     }
                     int *pdst = reinterpret_cast<int *>(sm + (hh == 0 ? OFF_PART0 + (i & 1) * PART_ROW : OFF_PART1 + i3 * PART_ROW)) + 7 + m;
+                    if (!(EXP & 1)) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) pdst[t * PW] = acc[t];
+                    }
                 }
                 lap(1);
                 if (i + 1 < niter) {
-                    if (hh == 1) im2col(R1 + 1, (i + 1) & 1);
+                    if (!(EXP & 4) && hh == 1) im2col(R1 + 1, (R1p + 1) & 1);
                     fence_proxy_async_smem();
                     fence_before_sync();
                     __syncwarp();
@@ -511,7 +508,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     fence_before_sync();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tm, TM_COLS);
-    if (tid == 0 && *s_fail) printf("qv fused kernel: mbarrier wait timed out in block %d\n", blockIdx.x);
+    if (tid == 0 && *s_fail)
+        printf(*s_fail == 2 ? "qv fused kernel: block %d has other shared-memory / TMEM bases than the descriptor table was built for\n"
+                            : "qv fused kernel: mbarrier wait timed out in block %d\n", blockIdx.x);
+}
+
+// Shared-memory window base and TMEM base a CTA of k_fused sees (same launch shape: dynamic smem only, all 512 columns).
+__global__ void k_bases(uint32_t *out)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint32_t *slot = reinterpret_cast<uint32_t *>(sm);
+    tmem_alloc(slot, TM_COLS);
+    tmem_relinquish();
+    fence_before_sync();
+    __syncwarp();
+    fence_after_sync();
+    const uint32_t tm = *slot;
+    if (threadIdx.x == 0) { out[0] = smem_u32(sm); out[1] = tm; }
+    __syncwarp();
+    tmem_dealloc(tm, TM_COLS);
+}
+
+// The operand list of one iteration, in issue order (see the MMA warp), for every phase R1 mod 12.
+void build_mma_table(uint32_t sb, uint32_t tm, MmaEntry (*tab)[N_MMA + 1])
+{
+    constexpr uint32_t LP = (uint32_t)(PLANE >> 4) << 16;                  // LBO = one plane: K-halves are planes p, p+1
+    constexpr uint32_t LX = 1u << 16;                                      // LBO = 16 B: K-halves are pixels x, x+1 of one plane
+    const uint32_t zeroA = sb + (OFF_ZERO >> 4) + ((128u * 16 >> 4) << 16);
+    const uint32_t anyB = sb + (OFF_W1 >> 4) + (64u << 16);
+    const uint32_t w1 = sb + (OFF_W1 >> 4) + (64u << 16);
+    const uint32_t w22 = sb + (OFF_W22 >> 4) + ((uint32_t)NR22 << 16), w21 = sb + (OFF_W21 >> 4) + ((uint32_t)NR21 << 16);
+    const uint32_t w31 = sb + (OFF_W31 >> 4) + ((uint32_t)NR31 << 16), w32 = sb + (OFF_W32 >> 4) + ((uint32_t)NR32 << 16);
+    for (int ph = 0; ph < N_PHASE; ++ph) {
+        const int R1p = ph + 4096 / N_PHASE * N_PHASE + N_PHASE, c3 = ph % 3, c6 = ph % 6;     // R1p = R1 (mod 12), large enough for R1p - k > 0
+        const uint32_t par = ph & 1;
+        const int qa = wrap_sub(c6, 2, 6);                                            // (R1-2) mod 6
+        const uint32_t a1_r2 = sb + (OFF_A1 >> 4) + wrap_sub(c3, 2, 3) * (A1_ROW >> 4) + LP;   // a1 row R1-2 (C2_2, C2_1)
+        const uint32_t a2_r6 = sb + (OFF_A2 >> 4) + c3 * (A2_ROW >> 4);                        // a2 row R1-6 (C3_1, C3_2)
+        const uint32_t b22 = w22 + (qa <= 2 ? 2 - qa : 8 - qa) * 16;         // window start (8 - qa) mod 6 blocks of 16 rows
+        const uint32_t b21 = w21 + ((1 - (R1p - 2)) & 3) * 32;               // (1 - (R1-2) mod 4) mod 4 blocks of 32 rows
+        const uint32_t b31 = w31 + ((1 - (R1p - 6)) & 3) * 16;
+        const uint32_t d1 = tm + TM_D1 + par * 64, d32 = tm + TM_D32 + par * 32;
+        const uint32_t im = sb + ((OFF_IM + par * IM_BYTES) >> 4) + ((128u * 16 >> 4) << 16);
+        int k = 0;
+        auto put = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo) { tab[ph][k++] = MmaEntry{a_lo, b_lo, d, 0}; };
+        put(d1, im, w1);                                                        // C1
+        put(tm + TM_R22 + c6 * 16, zeroA, anyB);                                // C2_2 row R1   starts: zero its slot
+        put(tm + TM_R21 + ((R1p - 1) & 3) * 32, zeroA, anyB);                   // C2_1 row R1-1 starts
+        put(tm + TM_R31 + ((R1p - 5) & 3) * 16, zeroA, anyB);                   // C3_1 row R1-5 starts
+        for (int t = 0; t < 10; ++t) {                                          // t = s*2 + h
+            const int s = t / 2, h = t & 1;
+            const uint32_t a = a1_r2 + ((h * 2 * PLANE + (4 + s) * 16) >> 4);
+            put(tm + TM_R22, a, b22 + t * (T22 >> 4));
+            if (s >= 1 && s <= 3) put(tm + TM_R21, a, b21 + ((s - 1) * 2 + h) * (T21 >> 4));
+        }
+        put(tm + TM_R31, a2_r6 + 6 + LP, b31);
+        put(tm + TM_R31, a2_r6 + 7 + LP, b31 + (T31 >> 4));
+        put(d32, a2_r6 + 7 + LP, w32);
+        put(tm + TM_R31, a2_r6 + 8 + LP, b31 + 2 * (T31 >> 4));
+        put(tm + TM_R31, a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, b31 + 3 * (T31 >> 4));
+        put(d32, a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, w32 + (T32 >> 4));
+        put(tm + TM_R31, a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, b31 + 4 * (T31 >> 4));
+        if (k != N_MMA) abort();
+    }
 }
 
 }  // namespace
@@ -638,6 +697,26 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_bases, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) {
+        // descriptor table in constant memory, for the shared-memory / TMEM bases a CTA of this launch shape gets
+        uint32_t *d_b = nullptr, h_b[2] = {0, 0};
+        e = cudaMalloc(&d_b, 8);
+        if (e == cudaSuccess) {
+            k_bases<<<1, 32, SMEM_BYTES, st>>>(d_b);
+            e = cudaMemcpyAsync(h_b, d_b, 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(d_b);
+        }
+        if (e == cudaSuccess) {
+            static MmaEntry tab[N_PHASE][N_MMA + 1];
+            memset(tab, 0, sizeof(tab));
+            build_mma_table(h_b[0] >> 4, h_b[1], tab);
+            P.sbase16 = h_b[0] >> 4; P.tmem_base = h_b[1];
+            e = cudaMemcpyToSymbolAsync(c_mma, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
     int dev = 0, sms = 148;
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

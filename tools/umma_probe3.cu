@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -227,6 +228,235 @@ static void thr_case(long long *dC, int *dSt)
     }
 }
 
+
+// ---- contention: what slows a back-to-back MMA stream down? ------------------------------------------
+// Thread 0 (warp 0, SM sub-partition 0) issues pairs (N=96 fill, N=128 lastuse) as in the fused kernel.  `nh`
+// hammer warps, placed on sub-partition `sp` (warp % 4 == sp) or spread over all four (sp < 0), run one of:
+//   1 ld.shared 128 B wavefronts   2 st.shared.v4 (512 B per warp instruction)   3 tcgen05.ld 32x32b.x16
+//   4 integer ALU only (IMAD / VIADDMNMX-like chains, 8 independent)             5 mbarrier.try_wait polling
+template <int MODE>
+__global__ void k_cont(int outer, long long *cycles, int *status, int nh, int sp)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sA = sm, *sB = sm + 32768;
+    uint8_t *scratch = sm + 32768 + 8192;        // 16 KB for the st.shared hammer
+    __shared__ uint64_t bar, bar2;
+    __shared__ uint32_t s_tmem;
+    __shared__ volatile int s_stop;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (32768 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sm)[i] = 0x01010101u * (i & 3);
+    fence_proxy_async_smem();
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_fence_init(); s_stop = 0; }
+    if (warp == 0) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = s_tmem;
+    // which warps hammer: warps 1.. ; on sub-partition sp only, or all
+    bool hammer = false;
+    if (warp >= 1) {
+        if (sp < 0) hammer = warp <= nh;
+        else hammer = (warp & 3) == sp && (warp >> 2) >= (sp == 0 ? 1 : 0) && ((warp >> 2) - (sp == 0 ? 1 : 0)) < nh;
+    }
+    if (tid == 0) {
+        constexpr uint32_t id1 = idesc_i8(128, 96, 1, 1), id2 = idesc_i8(128, 128, 1, 1);
+        const uint64_t bd1 = smem_desc(smem_u32(sB), 128 * 16, 128), bd2 = smem_desc(smem_u32(sB) + 16 * 16, 128 * 16, 128);
+        const uint64_t ad0 = smem_desc(smem_u32(sA), 16384, 128);
+        long long t0 = clock64();
+        for (int o = 0; o < outer; ++o) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint64_t a = ad0 + (uint64_t)((j * 37) % 800);
+                mma_col<1>(tm, a, bd1, id1, 1);
+                mma_col<3>(tm + 128, a, bd2, id2, 1);
+            }
+        }
+        long long t1 = clock64();
+        mma_commit(&bar);
+        const bool ok = mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        cycles[0] = t1 - t0;
+        cycles[1] = t2 - t0;
+        status[0] = ok ? 0 : 1;
+        s_stop = 1;
+    } else if (hammer) {
+        long long n = 0;
+        uint32_t acc = lane;
+        if (MODE == 1) {
+            const volatile uint32_t *p = reinterpret_cast<const volatile uint32_t *>(sm) + lane;
+            while (!s_stop) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += p[u * 32];
+                n += 8;
+            }
+        } else if (MODE == 2) {
+            uint4 *p = reinterpret_cast<uint4 *>(scratch) + (warp & 7) * 64 + lane;
+            while (!s_stop) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) { p[u * 32] = make_uint4(acc, n, u, 1); }
+                asm volatile("" ::: "memory");
+                n += 8;           // 2 x 4 wavefronts
+            }
+        } else if (MODE == 3) {
+            const uint32_t ta = tm + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+            while (!s_stop) {
+                uint32_t r[16];
+                tmem_ld_x16(ta + ((n & 7) * 16), r);
+                tmem_ld_wait();
+                acc += r[0] + r[15];
+                n += 1;
+            }
+        } else if (MODE == 4) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = acc + u;
+            while (!s_stop) {
+#pragma unroll
+                for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = v[u] * 1664525u + (v[(u + 1) & 7] >> 3);
+                n += 32;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        } else if (MODE == 6) {          // IADD3 / LOP3 only (alu pipe)
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = acc + u;
+            while (!s_stop) {
+#pragma unroll
+                for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = (v[u] + v[(u + 1) & 7]) ^ (v[(u + 3) & 7] | 0x55u);
+                n += 32;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        } else if (MODE == 7) {          // FFMA only
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (float)(acc + u);
+            while (!s_stop) {
+#pragma unroll
+                for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = fmaf(v[u], 1.0001f, v[(u + 1) & 7]);
+                n += 32;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += (uint32_t)v[u];
+        } else if (MODE == 8) {          // IDP.4A only
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (int)(acc + u);
+            while (!s_stop) {
+#pragma unroll
+                for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = __dp4a(v[(u + 1) & 7], 0x01020304, v[u]);
+                n += 32;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += (uint32_t)v[u];
+        } else if (MODE == 9) {          // the requantiser mix: VIADDMNMX.RELU + IMAD + PRMT
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = acc + u;
+            while (!s_stop) {
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = (uint32_t)__viaddmin_s32_relu((int)v[u], 37 + u, 19000) * 6431u;
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) v[u] = __byte_perm(v[u], v[u + 1], 0x0073);
+                }
+                n += 40;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        } else if (MODE == 5) {
+            while (!s_stop) {
+                acc += mbar_try_wait(&bar2, 0) ? 1u : 0u;      // never completes: every call is a (suspended) poll
+                n += 1;
+            }
+        }
+        if (acc == 0x12345678u) cycles[7] = acc;
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&cycles[2]), (unsigned long long)n);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+template <int MODE>
+static void cont_case(long long *dC, int *dSt, int nh, int sp)
+{
+    static const char *names[] = {"", "ld.shared", "st.shared.v4", "tcgen05.ld.x16", "IMAD chain", "mbarrier poll", "IADD3/LOP3", "FFMA", "IDP.4A", "requant mix"};
+    const int smem = 32768 + 8192 + 16384;
+    CK(cudaFuncSetAttribute(k_cont<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    long long c[4]; int st = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaMemset(dSt, 0, 4));
+        CK(cudaMemset(dC, 0, 64));
+        k_cont<MODE><<<1, 17 * 32, smem>>>(64, dC, dSt, nh, sp);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("cont: CUDA error %s\n", cudaGetErrorString(e)); exit(2); }
+    }
+    CK(cudaMemcpy(c, dC, 32, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost));
+    printf("cont %-15s x%2d warps on %-18s: %.1f cyc per (N=96,N=128) pair [112 alone]; hammer ops/clk %.3f timeout=%d\n", names[MODE], nh,
+           sp < 0 ? "all sub-partitions" : sp == 0 ? "the MMA warp's SMSP" : "another SMSP", (double)c[1] / (64 * 16), (double)c[2] / (double)c[1], st);
+}
+
+// ---- queue depth: how long does the issuing thread take to hand k MMAs to an idle tensor pipe? --------
+template <int K, int N>
+__global__ void k_burst(long long *cycles, int *status)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sA = sm, *sB = sm + 32768;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (32768 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sm)[i] = 0x01010101u * (i & 3);
+    fence_proxy_async_smem();
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = s_tmem;
+    if (tid == 0) {
+        constexpr uint32_t id = idesc_i8(128, N, 1, 1);
+        const uint64_t bd = smem_desc(smem_u32(sB), 128 * 16, 128);
+        const uint64_t ad0 = smem_desc(smem_u32(sA), 16384, 128);
+        long long t0 = clock64();
+#pragma unroll
+        for (int j = 0; j < K; ++j) mma_col<0>(tm, ad0 + (uint64_t)((j * 37) % 800), bd, id, 1);
+        long long t1 = clock64();
+        mma_commit(&bar);
+        const bool ok = mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        cycles[0] = t1 - t0;
+        cycles[1] = t2 - t0;
+        status[0] = ok ? 0 : 1;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+template <int K, int N>
+static void burst_case(long long *dC, int *dSt)
+{
+    CK(cudaFuncSetAttribute(k_burst<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8192));
+    long long c[2]; int st = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaMemset(dSt, 0, 4));
+        k_burst<K, N><<<1, 128, 32768 + 8192>>>(dC, dSt);
+        CK(cudaDeviceSynchronize());
+    }
+    CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost));
+    printf("burst N=%3d k=%2d MMAs: issued after %lld cycles, complete (commit seen) after %lld  timeout=%d\n", N, K, c[0], c[1], st);
+}
+
 int main(int argc, char **argv)
 {
     cudaDeviceProp p;
@@ -242,6 +472,29 @@ int main(int argc, char **argv)
         thr_case<64, 32, 0>(dC, dSt); thr_case<64, 32, 1>(dC, dSt); thr_case<64, 32, 3>(dC, dSt);
         thr_case<16, 32, 0>(dC, dSt); thr_case<16, 32, 1>(dC, dSt);
         thr_case<96, 96, 0>(dC, dSt); thr_case<96, 96, 1>(dC, dSt);
+    }
+    if (!strcmp(t, "cont") || !strcmp(t, "all")) {
+        long long *dC; int *dSt;
+        CK(cudaMalloc(&dC, 64)); CK(cudaMalloc(&dSt, 4));
+        cont_case<4>(dC, dSt, 0, 0);
+        cont_case<1>(dC, dSt, 8, -1); cont_case<1>(dC, dSt, 2, 0); cont_case<1>(dC, dSt, 2, 1);
+        cont_case<2>(dC, dSt, 8, -1); cont_case<2>(dC, dSt, 2, 0); cont_case<2>(dC, dSt, 2, 1);
+        cont_case<3>(dC, dSt, 8, -1); cont_case<3>(dC, dSt, 16, -1); cont_case<3>(dC, dSt, 2, 0); cont_case<3>(dC, dSt, 2, 1);
+        cont_case<4>(dC, dSt, 8, -1); cont_case<4>(dC, dSt, 16, -1); cont_case<4>(dC, dSt, 1, 0); cont_case<4>(dC, dSt, 2, 0); cont_case<4>(dC, dSt, 3, 0); cont_case<4>(dC, dSt, 2, 1);
+        cont_case<5>(dC, dSt, 8, -1); cont_case<5>(dC, dSt, 2, 0);
+    }
+    if (!strcmp(t, "burst") || !strcmp(t, "all")) {
+        long long *dC; int *dSt;
+        CK(cudaMalloc(&dC, 64)); CK(cudaMalloc(&dSt, 4));
+        burst_case<1, 128>(dC, dSt); burst_case<2, 128>(dC, dSt); burst_case<4, 128>(dC, dSt); burst_case<8, 128>(dC, dSt);
+        burst_case<16, 128>(dC, dSt); burst_case<32, 128>(dC, dSt); burst_case<64, 128>(dC, dSt);
+        burst_case<1, 32>(dC, dSt); burst_case<4, 32>(dC, dSt); burst_case<8, 32>(dC, dSt); burst_case<16, 32>(dC, dSt); burst_case<32, 32>(dC, dSt);
+    }
+    if (!strcmp(t, "cont2")) {
+        long long *dC; int *dSt;
+        CK(cudaMalloc(&dC, 64)); CK(cudaMalloc(&dSt, 4));
+        cont_case<4>(dC, dSt, 2, 0); cont_case<6>(dC, dSt, 2, 0); cont_case<7>(dC, dSt, 2, 0); cont_case<8>(dC, dSt, 2, 0); cont_case<9>(dC, dSt, 2, 0);
+        cont_case<9>(dC, dSt, 1, 0); cont_case<9>(dC, dSt, 4, 0); cont_case<9>(dC, dSt, 2, 1);
     }
     return 0;
 }
