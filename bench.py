@@ -43,6 +43,20 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel on this workload, from the committed
+    `ncu --set full` capture (profiles/ncu_fused_traffic.json, written by tools/ncu_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_fused_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("workload") != WORKLOAD:
+            return None
+        return {"dram_bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"], "algorithmic_bytes_per_launch": FRAMES * H * W * HBM_BYTES_PER_PIXEL,
+                "unit": "B", "source": d.get("source")}
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one streaming nvidia-smi
     process at 50 ms period; only lines that arrive between start() and stop() are kept)."""
@@ -289,8 +303,8 @@ def main():
             "e2e": {"value": e2e_mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": npx, "d2h_bytes_per_step": npx,
                     "api": "qv_forward_frames_host (pinned host in/out)", "bit_identical_to_device_path": same},
             "roofline": {"bound": "tensor", "achieved": tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": tops / int8_peak,
-                         "traffic": None, "peak_source": "2 x bf16_tflops_sustained, " + peaks["source"],
-                         "frac_of_nominal_4500": tops / 4500.0,
+                         "traffic": ncu_traffic(), "peak_source": "2 x bf16_tflops_sustained, " + peaks["source"],
+                         "frac_of_2x_bf16_burst": tops / (2.0 * peaks["bf16_burst"]), "frac_of_nominal_4500": tops / 4500.0,
                          "hbm": {"achieved_gbs": per_gpu_px_s * HBM_BYTES_PER_PIXEL / 1e9, "peak_gbs": peaks["hbm_gbs"],
                                  "frac": per_gpu_px_s * HBM_BYTES_PER_PIXEL / 1e9 / peaks["hbm_gbs"]},
                          "kernel_ms_per_launch": total_ms / max(1, launches)},

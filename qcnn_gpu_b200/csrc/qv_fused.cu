@@ -54,15 +54,6 @@
 #include "qv_fused.h"
 #include "qv_tcgen05.cuh"
 
-#ifndef QV_C4_LATE
-#define QV_C4_LATE 0
-#endif
-#ifndef QV_BIG_LAST
-#define QV_BIG_LAST 0
-#endif
-#ifndef QV_PRE_WAIT
-#define QV_PRE_WAIT 0
-#endif
 
 #ifndef QV_EXP
 #define QV_EXP 0
@@ -98,16 +89,13 @@ constexpr int OFF_A2 = OFF_A1 + A_SLOTS * A1_ROW;
 constexpr int OFF_IM = OFF_A2 + A_SLOTS * A2_ROW;
 constexpr int OFF_ZERO = OFF_IM + 2 * IM_BYTES;   // three im2col stages: stage (i+1)%3 is written while C1 of iteration i-1 may still read (i-1)%3
 constexpr int OFF_IN = OFF_ZERO + ZERO_BYTES;
-constexpr int PART_ROW = 9 * PW * 4;                 // C4 partial dot products of one a3 row: [tap][pixel] int32
-constexpr int OFF_PART0 = OFF_IN + IN_SLOTS * IN_PITCH;    // channels 0-15  (warps 0-3): [iteration & 1][tap][pixel]
-constexpr int OFF_PART1 = OFF_PART0 + 2 * PART_ROW;        // channels 16-47 (warps 4-7): [iteration % 3][tap][pixel], one row ahead
-constexpr int OFF_CTRL = OFF_PART1 + 3 * PART_ROW;
+constexpr int OFF_A3 = (OFF_IN + IN_SLOTS * IN_PITCH + 15) / 16 * 16;   // a3 rows for the C4 warps: 3 slots x [3 planes][pixel][16 B]
+constexpr int OFF_CTRL = OFF_A3 + A_SLOTS * A2_ROW;
 constexpr int SMEM_BYTES = OFF_CTRL + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
-constexpr int NWORKER = 256, NTHREADS = NWORKER + 32;
+constexpr int NWORKER = 256, NC4 = 128, NTHREADS = NWORKER + 32 + NC4;   // warps 0-7 workers, 8 MMA issue, 9-12 C4
 constexpr int TR_ITER0 = 300, TR_N = 8;    // profile-mode timeline window
-constexpr bool C4_LATE = QV_C4_LATE;      // workers: a3 -> C4 after (1) or before (0) the arrive that releases the next MMAs
 constexpr int PIPE = 14;                   // pipeline depth in rows: output row y0 appears at iteration 14
 
 // ---- TMEM columns (int32 accumulators) -------------------------------------------------------------
@@ -201,14 +189,21 @@ __device__ __forceinline__ void requant_store(const uint32_t (&r)[16], const Fus
     else requant<FAST, BOFF>(r, P, g, valid, o);
     *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
-// C4 (48 -> 1, 3x3) partial dot products of one pixel's 16 a3 channels (plane PL) with all nine taps
-template <int PL>
-__device__ __forceinline__ void c4_partials(const uint32_t (&o)[4], const FusedParams &P, int (&acc)[9])
+// C4 (48 -> 1, 3x3): the products of one a3 pixel (three 16-channel planes v[pl]) at horizontal tap DX with the three
+// vertical taps, added to acc[dy]
+template <int DX>
+__device__ __forceinline__ void c4_taps(const uint4 (&v)[3], const FusedParams &P, int (&acc)[3])
 {
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[t] = __dp4a((int)o[j], P.c4_w[(t * 3 + PL) * 4 + j], acc[t]);
+        for (int pl = 0; pl < 3; ++pl) {
+            const int *w = &P.c4_w[((dy * 3 + DX) * 3 + pl) * 4];
+            acc[dy] = __dp4a((int)v[pl].x, w[0], acc[dy]);
+            acc[dy] = __dp4a((int)v[pl].y, w[1], acc[dy]);
+            acc[dy] = __dp4a((int)v[pl].z, w[2], acc[dy]);
+            acc[dy] = __dp4a((int)v[pl].w, w[3], acc[dy]);
+        }
 }
 
 template <bool FAST, bool PROF>
@@ -328,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             }
         }
         if (PROF && P.dbg && leader) { P.dbg[blockIdx.x * 16 + 0] = t_wait; P.dbg[blockIdx.x * 16 + 1] = t_issue; }
-    } else {
+    } else if (warp < NWORKER / 32) {
         // ================================= workers =========================================
         const int q = warp & 3, hh = warp >> 2;
         const int m = q * 32 + lane;                              // this thread's MMA row / pixel
@@ -342,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 if (tr_slot >= 0 && k < 4) P.dbg[gridDim.x * 16 + tr_slot + k] = t;
             }
         };
-        auto worker_bar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };      // workers + C4 warps
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
             const int X0 = strip * WT;
@@ -388,9 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 ++ev_work;
             }
             int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
-            int i3 = 0;                                           // i mod 3: stage of the channels-16-47 partial-sum buffer
-            int c4_s1 = 0, c4_s2 = 0;
-            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6), i3 = wrap_inc(i3, 3)) {
+            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
                 const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
                 if (PROF)
@@ -407,33 +400,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     fence_after_sync();
                     lap(0);
                     const uint32_t par = (R1p - 1) & 1;         // D1 / D32 stage the MMAs of iteration i-1 wrote
-                    if (!(EXP & 1) && hh == 0 && i >= 2) {
-                        const int *part0 = reinterpret_cast<const int *>(sm + OFF_PART0 + ((i - 1) & 1) * PART_ROW) + 8 + m;
-                        const int *part1 = reinterpret_cast<const int *>(sm + OFF_PART1 + wrap_sub(i3, 2, 3) * PART_ROW) + 8 + m;
-                        int q[3];
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) {
-                            int v = 0;
-#pragma unroll
-                            for (int sft = 0; sft < 3; ++sft)
-                                v += part0[(r * 3 + sft) * PW + sft - 1] + part1[(r * 3 + sft) * PW + sft - 1];
-                            q[r] = v;
-                        }
-                        const int u4 = c4_s2 + q[2];
-                        c4_s2 = c4_s1 + q[1];
-                        c4_s1 = q[0];
-                        const int rowo = R1 - 10;
-                        if (rowo >= y0 && rowo < y1 && m < WT && X0 + m < W) {
-                            const int x = sm[OFF_IN + ((R1p - 10) & (IN_SLOTS - 1)) * IN_PITCH + 8 + m];
-                            outf[(size_t)rowo * W + X0 + m] = (uint8_t)residual_apply(u4 + P.c4_bias, x, P.c4_mul, P.c4_shift);
-                        }
-                    }
                     const bool xa1 = X0 - 4 + m >= 0 && X0 - 4 + m < W, xa2 = X0 - 2 + m >= 0 && X0 - 2 + m < W, xa3 = X0 - 1 + m >= 0 && X0 - 1 + m < W;
                     const bool v1 = R1 - 1 >= 0 && R1 - 1 < H && xa1;
                     uint8_t *dst1 = sm + OFF_A1 + wrap_sub(c3, 1, 3) * A1_ROW + (4 + m) * 16;
                     const uint32_t d1 = tm_lane + TM_D1 + par * 64;
-                    uint32_t ra[16], rb[16], rc[16], rd[16], re[16], o[4];
-                    int acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    uint32_t ra[16], rb[16], rc[16], rd[16], re[16];
                     if (hh == 0) {
                         const bool v2 = R1 - 5 >= 0 && R1 - 5 < H && xa2, v2n = R1 - 4 >= 0 && R1 - 4 < H && xa2;
                         const bool v3 = R1 - 8 >= 0 && R1 - 8 < H && xa3;
@@ -448,10 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         requant_store<FAST, 16>(rb, P, P.q1, v1, dst1 + 1 * PLANE);
                         requant_store<FAST, 64>(rc, P, P.q22, v2, dst2 + 2 * PLANE);
                         requant_store<FAST, 80>(rd, P, P.q21, v2n, dst2n + 0 * PLANE);
-                        if (!(EXP & 1)) {
-                        requant<FAST, 112>(re, P, P.q31, v3, o);
-                        c4_partials<0>(o, P, acc);
-                        }
+                        if (!(EXP & 1)) requant_store<FAST, 112>(re, P, P.q31, v3, sm + OFF_A3 + wrap_sub(c3, 8, 3) * A2_ROW + (7 + m) * 16);   // a3 row R1-8 plane 0
                     } else {
                         const bool v2n = R1 - 4 >= 0 && R1 - 4 < H && xa2;
                         const bool v3n = R1 - 7 >= 0 && R1 - 7 < H && xa3;
@@ -465,16 +433,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         requant_store<FAST, 48>(rb, P, P.q1, v1, dst1 + 3 * PLANE);
                         requant_store<FAST, 96>(rc, P, P.q21, v2n, dst2n + 1 * PLANE);
                         if (!(EXP & 1)) {
-                        requant<FAST, 128>(rd, P, P.q32, v3n, o);
-                        c4_partials<1>(o, P, acc);
-                        requant<FAST, 144>(re, P, P.q32, v3n, o);
-                        c4_partials<2>(o, P, acc);
+                            uint8_t *dst3n = sm + OFF_A3 + wrap_sub(c3, 7, 3) * A2_ROW + (7 + m) * 16;                      // a3 row R1-7 planes 1, 2
+                            requant_store<FAST, 128>(rd, P, P.q32, v3n, dst3n + 1 * PLANE);
+                            requant_store<FAST, 144>(re, P, P.q32, v3n, dst3n + 2 * PLANE);
                         }
-                    }
-                    int *pdst = reinterpret_cast<int *>(sm + (hh == 0 ? OFF_PART0 + (i & 1) * PART_ROW : OFF_PART1 + i3 * PART_ROW)) + 7 + m;
-                    if (!(EXP & 1)) {
-#pragma unroll
-                    for (int t = 0; t < 9; ++t) pdst[t * PW] = acc[t];
                     }
                 }
                 lap(1);
@@ -503,6 +465,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         {
             for (int k = 0; k < 6; ++k) P.dbg[blockIdx.x * 16 + 2 + (tid >> 7) * 6 + k] = tw[k];
             P.dbg[blockIdx.x * 16 + 14 + (tid >> 7)] = t_ldtm;
+        }
+    } else {
+        // ================================= C4 warps ==========================================
+        // The last layer (3x3, 48 -> 1) and the reconstruction, on CUDA cores and off everybody's critical path: these four
+        // warps only meet the workers at the named barrier that ends an iteration.  Thread mo owns output column X0 + mo.
+        // Iteration i takes a3 row r = R1-9 (its plane 0 was stored one iteration ago, planes 1 and 2 two iterations ago):
+        // for each horizontal tap dx the pixel's 48 channels are multiplied with the three vertical taps, which belong to
+        // the output rows r+1 (dy = 0), r (dy = 1) and r-1 (dy = 2); two running sums carry the partial rows, and row
+        // r-1 = R1-10 is complete: applyRes_y (cnn.cu:507-523) and the store.
+        const int mo = tid - (NWORKER + 32);
+        auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };
+        for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
+            const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
+            const int X0 = strip * WT;
+            const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
+            const int niter = y1 - y0 + PIPE;
+            uint8_t *outf = P.out + (size_t)f * H * W;
+            const bool col_ok = mo < WT && X0 + mo < W;
+            int c3 = mod_pos(y0 - 4, 3);
+            int c4_s1 = 0, c4_s2 = 0;
+            worker_bar();                                         // the workers' prologue barrier
+            for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3)) {
+                const int R1 = y0 - 4 + i, R1p = R1 + 4096;
+                if (!(EXP & 1) && !(P.dbg_flags & 2) && i >= 3) {
+                    const uint8_t *row = sm + OFF_A3 + c3 * A2_ROW + (7 + mo) * 16;      // slot (R1-9) mod 3 = R1 mod 3, pixel 7 + mo + dx
+                    int acc[3] = {0, 0, 0};
+                    uint4 v[3];
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) v[pl] = *reinterpret_cast<const uint4 *>(row + pl * PLANE);
+                    c4_taps<0>(v, P, acc);
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) v[pl] = *reinterpret_cast<const uint4 *>(row + pl * PLANE + 16);
+                    c4_taps<1>(v, P, acc);
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) v[pl] = *reinterpret_cast<const uint4 *>(row + pl * PLANE + 32);
+                    c4_taps<2>(v, P, acc);
+                    const int u4 = c4_s2 + acc[2];                // out row y: a3 rows y-1 (tap row 0), y (1), y+1 (2)
+                    c4_s2 = c4_s1 + acc[1];
+                    c4_s1 = acc[0];
+                    const int rowo = R1 - 10;
+                    if (rowo >= y0 && rowo < y1 && col_ok) {
+                        const int x = sm[OFF_IN + ((R1p - 10) & (IN_SLOTS - 1)) * IN_PITCH + 8 + mo];
+                        outf[(size_t)rowo * W + X0 + mo] = (uint8_t)residual_apply(u4 + P.c4_bias, x, P.c4_mul, P.c4_shift);   // cnn.cu:507-523
+                    }
+                }
+                worker_bar();
+            }
+            worker_bar();                                         // the workers' drain barrier
         }
     }
     fence_before_sync();

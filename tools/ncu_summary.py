@@ -14,3 +14,14 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 for h, u, v in zip(hdr, units, vals):
     if h in want:
         print("%-75s %-12s %s" % (h, u, v))
+
+# machine-readable DRAM traffic of the launch, for bench.py's roofline.traffic
+if len(sys.argv) > 2:
+    import json
+    d = dict(zip(hdr, vals)); un = dict(zip(hdr, units))
+    def to_bytes(k):
+        v = float(d[k]); u = un[k].lower()
+        return int(v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u])
+    json.dump({"workload": "config3: QVRCNN QP=32, 64x1920x1080 synthetic luma frames per GPU", "dram_bytes_read": to_bytes("dram__bytes_read.sum"),
+               "dram_bytes_write": to_bytes("dram__bytes_write.sum"), "kernel": d["Kernel Name"], "source": sys.argv[3] if len(sys.argv) > 3 else rep},
+              open(sys.argv[2], "w"), indent=1)
