@@ -132,9 +132,15 @@ struct FusedParams {
 // loads only: measured (profiles/r1_probe3_contention*.log), integer ALU work of the worker warps that share the MMA
 // warp's SM sub-partition starves exactly the ALU-pipe instructions (address arithmetic, R2UR) an issue loop would
 // otherwise need, and the tensor pipe's queue is only a handful of instructions deep.
-struct MmaEntry { uint32_t a_lo, b_lo, d, pad; };       // low descriptor words (16-byte units | LBO << 16), TMEM address
-constexpr int N_MMA = 27, N_PHASE = 12;
-__constant__ MmaEntry c_mma[N_PHASE][N_MMA + 1];
+struct PhaseBases {                    // low descriptor words (16-byte units | LBO << 16) and TMEM addresses that rotate with R1
+    uint32_t im, a1_r2, a2_r6, b22;    // C1 operand stage ; a1 row R1-2 ; a2 row R1-6 ; C2_2 ring window start
+    uint32_t b21, b31, d1, d32;        // C2_1 / C3_1 ring window starts ; C1 / C3_2 accumulator stages
+    uint32_t z22, z21, z31, pad;       // ring slots of the rows that start in this iteration
+};
+struct FixedBases { uint32_t zeroA, w1, w32, r22, r21, r31, pad0, pad1; };   // what does not rotate
+constexpr int N_PHASE = 12;
+__constant__ PhaseBases c_phase[N_PHASE];
+__constant__ FixedBases c_fixed;
 
 __host__ __device__ __forceinline__ int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
@@ -263,14 +269,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         constexpr std::integral_constant<int, COL_FILL> KEEP{};                // A tile stays in the collector ...
         constexpr std::integral_constant<int, COL_USE> AGAIN{};                // ... is used from there and kept ...
         constexpr std::integral_constant<int, COL_LASTUSE> LAST{};             // ... and used from there for the last time
-        if ((sbase >> 4) != P.sbase16 || tm != P.tmem_base) { if (lane == 0) *s_fail = 2; }     // c_mma does not describe this CTA
+        if ((sbase >> 4) != P.sbase16 || tm != P.tmem_base) { if (lane == 0) *s_fail = 2; }     // c_phase / c_fixed do not describe this CTA
+        constexpr uint32_t LP = (uint32_t)(PLANE >> 4) << 16;                  // LBO = one plane: K-halves are planes p, p+1
+        constexpr uint32_t LX = 1u << 16;                                      // LBO = 16 B: K-halves are pixels x, x+1 of one plane
+        const FixedBases fb = c_fixed;
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg;
             const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             int ph = mod_pos(y0 - 4, N_PHASE);
-            for (int i = 0; i < niter; ++i, ph = wrap_inc(ph, N_PHASE)) {
-                const MmaEntry *tab = c_mma[ph];
+            PhaseBases pb_next = c_phase[ph];
+            for (int i = 0; i < niter; ++i) {
+                const PhaseBases pb = pb_next;                    // this iteration's operand bases (loaded one iteration ago)
                 warp_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1, lane, s_fail);
                 ++ev_work;
                 fence_after_sync();
@@ -281,38 +291,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 0] = tc0;
                     stamp = tr ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
                 }
-                int k = 0;
-                auto T = [&](auto col, uint32_t idesc, uint32_t acc) { MMA(col, tab[k].d, tab[k].a_lo, tab[k].b_lo, idesc, acc); ++k; };
                 // ---- C1: a1 row R1 = im2col[R1 & 1] x W1 (N = 64) --------------------------------------
-                T(ONCE, idesc_i8(128, 64), 0);
+                MMA(ONCE, pb.d1, pb.im, fb.w1, idesc_i8(128, 64), 0);
                 // ---- the ring slots of the rows that start in this iteration: 0 = zero tile x anything ------
-                T(KEEP, idesc_i8(128, 16), 0);        // C2_2 row R1
-                T(AGAIN, idesc_i8(128, 32), 0);       // C2_1 row R1-1
-                T(LAST, idesc_i8(128, 16), 0);        // C3_1 row R1-5
+                MMA(KEEP, pb.z22, fb.zeroA, fb.w1, idesc_i8(128, 16), 0);        // C2_2 row R1
+                MMA(AGAIN, pb.z21, fb.zeroA, fb.w1, idesc_i8(128, 32), 0);       // C2_1 row R1-1
+                MMA(LAST, pb.z31, fb.zeroA, fb.w1, idesc_i8(128, 16), 0);        // C3_1 row R1-5
                 // ---- layer 2: scatter a1 row R1-2.  C2_2 (5x5, 64 -> 16) into its 6-slot ring with N = 96, shifts
                 //      s = 0..4 (pixel 4+s) x K-halves h (planes 2h, 2h+1); C2_1 (3x3, 64 -> 32) into its 4-slot
                 //      ring with N = 128 reads the same tile for s = 1..3 and takes it from the collector ------------
 #pragma unroll
                 for (int t = 0; t < 10; ++t) {
-                    const int s = t / 2;
+                    const int s = t / 2, h = t & 1;
+                    const uint32_t a = pb.a1_r2 + ((h * 2 * PLANE + (4 + s) * 16) >> 4);
                     if (s >= 1 && s <= 3) {
-                        T(KEEP, idesc_i8(128, 96), 1);
-                        T(LAST, idesc_i8(128, 128), 1);
+                        MMA(KEEP, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
+                        MMA(LAST, fb.r21, a, pb.b21 + ((s - 1) * 2 + h) * (T21 >> 4), idesc_i8(128, 128), 1);
                     } else {
-                        T(ONCE, idesc_i8(128, 96), 1);
+                        MMA(ONCE, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
                     }
                 }
                 // ---- layer 3 on a2 row R1-6.  C3_1 (3x3, 48 -> 16) scatters into its 4-slot ring, N = 64; its K-steps
                 //      pair 16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights).
                 //      C3_2 (1x1, 48 -> 32, N = 32) needs exactly the tiles of K-steps 1 and 3 (centre pixel: planes 0,1
                 //      and zero weights | plane 2) and takes them from the collector -------------------------------------
-                T(ONCE, idesc_i8(128, 64), 1);
-                T(KEEP, idesc_i8(128, 64), 1);
-                T(LAST, idesc_i8(128, 32), 0);
-                T(ONCE, idesc_i8(128, 64), 1);
-                T(KEEP, idesc_i8(128, 64), 1);
-                T(LAST, idesc_i8(128, 32), 1);
-                T(ONCE, idesc_i8(128, 64), 1);
+                MMA(ONCE, fb.r31, pb.a2_r6 + 6 + LP, pb.b31, idesc_i8(128, 64), 1);
+                MMA(KEEP, fb.r31, pb.a2_r6 + 7 + LP, pb.b31 + (T31 >> 4), idesc_i8(128, 64), 1);
+                MMA(LAST, pb.d32, pb.a2_r6 + 7 + LP, fb.w32, idesc_i8(128, 32), 0);
+                MMA(ONCE, fb.r31, pb.a2_r6 + 8 + LP, pb.b31 + 2 * (T31 >> 4), idesc_i8(128, 64), 1);
+                MMA(KEEP, fb.r31, pb.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, pb.b31 + 3 * (T31 >> 4), idesc_i8(128, 64), 1);
+                MMA(LAST, pb.d32, pb.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, fb.w32 + (T32 >> 4), idesc_i8(128, 32), 1);
+                MMA(ONCE, fb.r31, pb.a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, pb.b31 + 4 * (T31 >> 4), idesc_i8(128, 64), 1);
+                ph = wrap_inc(ph, N_PHASE);
+                pb_next = c_phase[ph];                            // three 16-byte constant loads, in flight during the handshake
                 if (leader) mma_commit(&bar_mma[ev_mma & 1]);
                 ++ev_mma;
                 __syncwarp();
@@ -539,47 +550,33 @@ __global__ void k_bases(uint32_t *out)
     tmem_dealloc(tm, TM_COLS);
 }
 
-// The operand list of one iteration, in issue order (see the MMA warp), for every phase R1 mod 12.
-void build_mma_table(uint32_t sb, uint32_t tm, MmaEntry (*tab)[N_MMA + 1])
+// The operand bases of one iteration for every phase R1 mod 12, and the ones that never change.
+void build_mma_bases(uint32_t sb, uint32_t tm, PhaseBases *pb, FixedBases &fb)
 {
     constexpr uint32_t LP = (uint32_t)(PLANE >> 4) << 16;                  // LBO = one plane: K-halves are planes p, p+1
-    constexpr uint32_t LX = 1u << 16;                                      // LBO = 16 B: K-halves are pixels x, x+1 of one plane
-    const uint32_t zeroA = sb + (OFF_ZERO >> 4) + ((128u * 16 >> 4) << 16);
-    const uint32_t anyB = sb + (OFF_W1 >> 4) + (64u << 16);
-    const uint32_t w1 = sb + (OFF_W1 >> 4) + (64u << 16);
     const uint32_t w22 = sb + (OFF_W22 >> 4) + ((uint32_t)NR22 << 16), w21 = sb + (OFF_W21 >> 4) + ((uint32_t)NR21 << 16);
-    const uint32_t w31 = sb + (OFF_W31 >> 4) + ((uint32_t)NR31 << 16), w32 = sb + (OFF_W32 >> 4) + ((uint32_t)NR32 << 16);
+    const uint32_t w31 = sb + (OFF_W31 >> 4) + ((uint32_t)NR31 << 16);
+    fb = FixedBases{};
+    fb.zeroA = sb + (OFF_ZERO >> 4) + ((128u * 16 >> 4) << 16);
+    fb.w1 = sb + (OFF_W1 >> 4) + (64u << 16);
+    fb.w32 = sb + (OFF_W32 >> 4) + ((uint32_t)NR32 << 16);
+    fb.r22 = tm + TM_R22; fb.r21 = tm + TM_R21; fb.r31 = tm + TM_R31;
     for (int ph = 0; ph < N_PHASE; ++ph) {
         const int R1p = ph + 4096 / N_PHASE * N_PHASE + N_PHASE, c3 = ph % 3, c6 = ph % 6;     // R1p = R1 (mod 12), large enough for R1p - k > 0
         const uint32_t par = ph & 1;
         const int qa = wrap_sub(c6, 2, 6);                                            // (R1-2) mod 6
-        const uint32_t a1_r2 = sb + (OFF_A1 >> 4) + wrap_sub(c3, 2, 3) * (A1_ROW >> 4) + LP;   // a1 row R1-2 (C2_2, C2_1)
-        const uint32_t a2_r6 = sb + (OFF_A2 >> 4) + c3 * (A2_ROW >> 4);                        // a2 row R1-6 (C3_1, C3_2)
-        const uint32_t b22 = w22 + (qa <= 2 ? 2 - qa : 8 - qa) * 16;         // window start (8 - qa) mod 6 blocks of 16 rows
-        const uint32_t b21 = w21 + ((1 - (R1p - 2)) & 3) * 32;               // (1 - (R1-2) mod 4) mod 4 blocks of 32 rows
-        const uint32_t b31 = w31 + ((1 - (R1p - 6)) & 3) * 16;
-        const uint32_t d1 = tm + TM_D1 + par * 64, d32 = tm + TM_D32 + par * 32;
-        const uint32_t im = sb + ((OFF_IM + par * IM_BYTES) >> 4) + ((128u * 16 >> 4) << 16);
-        int k = 0;
-        auto put = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo) { tab[ph][k++] = MmaEntry{a_lo, b_lo, d, 0}; };
-        put(d1, im, w1);                                                        // C1
-        put(tm + TM_R22 + c6 * 16, zeroA, anyB);                                // C2_2 row R1   starts: zero its slot
-        put(tm + TM_R21 + ((R1p - 1) & 3) * 32, zeroA, anyB);                   // C2_1 row R1-1 starts
-        put(tm + TM_R31 + ((R1p - 5) & 3) * 16, zeroA, anyB);                   // C3_1 row R1-5 starts
-        for (int t = 0; t < 10; ++t) {                                          // t = s*2 + h
-            const int s = t / 2, h = t & 1;
-            const uint32_t a = a1_r2 + ((h * 2 * PLANE + (4 + s) * 16) >> 4);
-            put(tm + TM_R22, a, b22 + t * (T22 >> 4));
-            if (s >= 1 && s <= 3) put(tm + TM_R21, a, b21 + ((s - 1) * 2 + h) * (T21 >> 4));
-        }
-        put(tm + TM_R31, a2_r6 + 6 + LP, b31);
-        put(tm + TM_R31, a2_r6 + 7 + LP, b31 + (T31 >> 4));
-        put(d32, a2_r6 + 7 + LP, w32);
-        put(tm + TM_R31, a2_r6 + 8 + LP, b31 + 2 * (T31 >> 4));
-        put(tm + TM_R31, a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, b31 + 3 * (T31 >> 4));
-        put(d32, a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, w32 + (T32 >> 4));
-        put(tm + TM_R31, a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, b31 + 4 * (T31 >> 4));
-        if (k != N_MMA) abort();
+        PhaseBases &e = pb[ph];
+        e = PhaseBases{};
+        e.im = sb + ((OFF_IM + par * IM_BYTES) >> 4) + ((128u * 16 >> 4) << 16);
+        e.a1_r2 = sb + (OFF_A1 >> 4) + wrap_sub(c3, 2, 3) * (A1_ROW >> 4) + LP;       // a1 row R1-2 (C2_2, C2_1)
+        e.a2_r6 = sb + (OFF_A2 >> 4) + c3 * (A2_ROW >> 4);                            // a2 row R1-6 (C3_1, C3_2)
+        e.b22 = w22 + (qa <= 2 ? 2 - qa : 8 - qa) * 16;                               // window start (8 - qa) mod 6 blocks of 16 rows
+        e.b21 = w21 + ((1 - (R1p - 2)) & 3) * 32;                                     // (1 - (R1-2) mod 4) mod 4 blocks of 32 rows
+        e.b31 = w31 + ((1 - (R1p - 6)) & 3) * 16;
+        e.d1 = tm + TM_D1 + par * 64; e.d32 = tm + TM_D32 + par * 32;
+        e.z22 = tm + TM_R22 + c6 * 16;                                                // C2_2 row R1   starts: zero its slot
+        e.z21 = tm + TM_R21 + ((R1p - 1) & 3) * 32;                                   // C2_1 row R1-1 starts
+        e.z31 = tm + TM_R31 + ((R1p - 5) & 3) * 16;                                   // C3_1 row R1-5 starts
     }
 }
 
@@ -719,11 +716,12 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
             cudaFree(d_b);
         }
         if (e == cudaSuccess) {
-            static MmaEntry tab[N_PHASE][N_MMA + 1];
-            memset(tab, 0, sizeof(tab));
-            build_mma_table(h_b[0] >> 4, h_b[1], tab);
+            PhaseBases pb[N_PHASE];
+            FixedBases fb;
+            build_mma_bases(h_b[0] >> 4, h_b[1], pb, fb);
             P.sbase16 = h_b[0] >> 4; P.tmem_base = h_b[1];
-            e = cudaMemcpyToSymbolAsync(c_mma, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
+            e = cudaMemcpyToSymbolAsync(c_phase, pb, sizeof(pb), 0, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_fixed, &fb, sizeof(fb), 0, cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         }
     }
@@ -807,6 +805,11 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
                 fprintf(stderr, "[qv fused trace] it %d | mma: start %lld end %lld | w0: commit %lld drained %lld arrived %lld bar %lld | "
                         "w4: commit %lld drained %lld arrived %lld bar %lld\n", TR_ITER0 + k, tr[0] - t0, tr[1] - t0, tr[2] - t0, tr[3] - t0,
                         tr[4] - t0, tr[5] - t0, tr[6] - t0, tr[7] - t0, tr[8] - t0, tr[9] - t0);
+        tr = h.data() + (size_t)grid * 16;
+        if (t0)
+            for (int k = 0; k < TR_N; ++k, tr += 16)
+                fprintf(stderr, "[qv fused mma-side] it %d | loop top %lld  wait done %lld  fence done %lld  (issue start %lld)  commit issued %lld  end %lld\n",
+                        TR_ITER0 + k, tr[10] - t0, tr[11] - t0, tr[12] - t0, tr[0] - t0, tr[13] - t0, tr[1] - t0);
         if (t0)
             for (int k = 0; k < TR_N; ++k) {
                 const long long *sp = h.data() + (size_t)grid * 16 + TR_N * 16 + k * 32, s0 = h[(size_t)grid * 16 + k * 16];
