@@ -87,7 +87,7 @@ constexpr int WIMG_BYTES = OFF_BIAS + BIAS_INTS * 4;         // what lives in gl
 constexpr int OFF_A1 = (WIMG_BYTES + 127) / 128 * 128;
 constexpr int OFF_A2 = OFF_A1 + A_SLOTS * A1_ROW;
 constexpr int OFF_IM = OFF_A2 + A_SLOTS * A2_ROW;
-constexpr int OFF_ZERO = OFF_IM + 2 * IM_BYTES;   // three im2col stages: stage (i+1)%3 is written while C1 of iteration i-1 may still read (i-1)%3
+constexpr int OFF_ZERO = OFF_IM + 3 * IM_BYTES;   // three im2col stages: stage (i+1)%3 is written while C1 of iteration i-1 may still read (i-1)%3
 constexpr int OFF_IN = OFF_ZERO + ZERO_BYTES;
 constexpr int OFF_A3 = (OFF_IN + IN_SLOTS * IN_PITCH + 15) / 16 * 16;   // a3 rows for the C4 warps: 3 slots x [3 planes][pixel][16 B]
 constexpr int OFF_CTRL = OFF_A3 + A_SLOTS * A2_ROW;
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     for (int i = tid; i < (OFF_CTRL - OFF_A1) / 16; i += NTHREADS)      // finite data everywhere the MMAs may read
         reinterpret_cast<uint4 *>(sm + OFF_A1)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        mbar_init(&bar_work[0], 8);
-        mbar_init(&bar_work[1], 8);
+        mbar_init(&bar_work[0], (NWORKER + NC4) / 32);          // every worker warp and every C4 warp arrives
+        mbar_init(&bar_work[1], (NWORKER + NC4) / 32);
         mbar_init(&bar_mma[0], 1);
         mbar_init(&bar_mma[1], 1);
         *s_fail = 0;
@@ -354,49 +354,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             const int X0 = strip * WT;
             const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
-            const uint8_t *inf = P.in + (size_t)f * H * W;
-            uint8_t *outf = P.out + (size_t)f * H * W;
-            const int col_in = X0 - 8 + tid;                      // input-ring byte this thread loads (tid < PW)
-            const bool in_col_ok = tid < PW && col_in >= 0 && col_in < W;
-            auto load_in = [&](int row) -> unsigned {
-                return (in_col_ok && row >= 0 && row < H) ? (unsigned)inf[(size_t)row * W + col_in] : 128u;
-            };
-            auto store_in = [&](int row, unsigned v) {
-                if (tid < PW) sm[OFF_IN + ((row + 4096) & (IN_SLOTS - 1)) * IN_PITCH + tid] = (uint8_t)v;
-            };
-            // im2col of input rows R-2..R+2 for a1 row R (threads of warps 4-7: pixel m)
-            auto im2col = [&](int R, int buf) {
-                uint32_t A[5], bcol = 0, b4 = 0;
-                const int p = m + 2, o8 = (p & 3) * 8;
-#pragma unroll
-                for (int r = 0; r < 5; ++r) {
-                    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm + OFF_IN + ((R + 4094 + r) & (IN_SLOTS - 1)) * IN_PITCH) + (p >> 2);
-                    const uint32_t w0 = rowp[0], w1 = rowp[1];
-                    A[r] = __funnelshift_r(w0, w1, o8);           // bytes p..p+3   (taps s = 0..3)
-                    const uint32_t b = (w1 >> o8) & 0xffu;        // byte  p+4      (tap  s = 4)
-                    if (r < 4) bcol |= b << (8 * r); else b4 = b;
-                }
-                // x - 128 as int8 == x ^ 0x80 (cnn.cu:450); K order: k = 4r+s (s<4), 20+r (s=4), 25..31 zero weights
-                uint8_t *dst = sm + OFF_IM + buf * IM_BYTES + m * 16;
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(A[0] ^ 0x80808080u, A[1] ^ 0x80808080u, A[2] ^ 0x80808080u, A[3] ^ 0x80808080u);
-                *reinterpret_cast<uint4 *>(dst + 128 * 16) = make_uint4(A[4] ^ 0x80808080u, bcol ^ 0x80808080u, b4 ^ 0x80u, 0u);
-            };
-
-            // ---- prologue: input rows for a1 rows y0-4 and y0-3, im2col of the first ------------
-            {
-                const int R1 = y0 - 4;
-                for (int r = R1 - 2; r <= R1 + 3; ++r) store_in(r, load_in(r));
-                worker_bar();
-                if (hh == 1) im2col(R1, R1 & 1);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
-                ++ev_work;
-            }
+            // ---- prologue: the previous unit's accumulators are drained (nothing of this unit is in flight yet) ------------
+            worker_bar();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+            ++ev_work;
             int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
-                const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
                 if (PROF)
                     tr_slot = (P.dbg && unit == 0 && (tid == 0 || tid == 128) && i >= TR_ITER0 && i < TR_ITER0 + TR_N)
                                   ? (i - TR_ITER0) * 16 + 2 + (tid >> 7) * 4 : -1;
@@ -452,7 +417,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 }
                 lap(1);
                 if (i + 1 < niter) {
-                    if (!(EXP & 4) && hh == 1) im2col(R1 + 1, (R1p + 1) & 1);
                     fence_proxy_async_smem();
                     fence_before_sync();
                     __syncwarp();
@@ -460,8 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     ++ev_work;
                 }
                 lap(2);
-                store_in(R1 + 4, in_next);
-                worker_bar();                                     // input ring visible to the im2col warps of the next iteration
+                worker_bar();                                     // a3 rows visible to the C4 warps
                 lap(3);
             }
             // drain: the MMAs of the last iteration still read smem / write TMEM
@@ -486,19 +449,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         // the output rows r+1 (dy = 0), r (dy = 1) and r-1 (dy = 2); two running sums carry the partial rows, and row
         // r-1 = R1-10 is complete: applyRes_y (cnn.cu:507-523) and the store.
         const int mo = tid - (NWORKER + 32);
+        uint32_t ev_work = 0;
         auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
             const int X0 = strip * WT;
             const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
+            const uint8_t *inf = P.in + (size_t)f * H * W;
             uint8_t *outf = P.out + (size_t)f * H * W;
             const bool col_ok = mo < WT && X0 + mo < W;
+            // The input ring: 136 bytes (image columns X0-8 ..) of 32 rows; thread mo loads byte mo, threads 0-7 also byte 128 + mo.
+            const int col_a = X0 - 8 + mo, col_b = col_a + 128;
+            const bool ok_a = col_a >= 0 && col_a < W, ok_b = mo < PW - 128 && col_b < W;
+            auto load_in = [&](int row) -> unsigned {
+                const bool rok = row >= 0 && row < H;
+                const uint8_t *rp = inf + (size_t)row * W;
+                const unsigned a = (rok && ok_a) ? (unsigned)rp[col_a] : 128u;
+                const unsigned b = (rok && ok_b) ? (unsigned)rp[col_b] : 128u;
+                return a | (b << 8);
+            };
+            auto store_in = [&](int row, unsigned v) {
+                uint8_t *rp = sm + OFF_IN + ((row + 4096) & (IN_SLOTS - 1)) * IN_PITCH;
+                rp[mo] = (uint8_t)v;
+                if (mo < PW - 128) rp[128 + mo] = (uint8_t)(v >> 8);
+            };
+            // im2col of input rows R-2..R+2 for a1 row R (pixel m = mo), the A operand of C1
+            const int m = mo;
+            auto im2col = [&](int R, int buf) {
+                uint32_t A[5], bcol = 0, b4 = 0;
+                const int p = m + 2, o8 = (p & 3) * 8;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm + OFF_IN + ((R + 4094 + r) & (IN_SLOTS - 1)) * IN_PITCH) + (p >> 2);
+                    const uint32_t w0 = rowp[0], w1 = rowp[1];
+                    A[r] = __funnelshift_r(w0, w1, o8);           // bytes p..p+3   (taps s = 0..3)
+                    const uint32_t b = (w1 >> o8) & 0xffu;        // byte  p+4      (tap  s = 4)
+                    if (r < 4) bcol |= b << (8 * r); else b4 = b;
+                }
+                // x - 128 as int8 == x ^ 0x80 (cnn.cu:450); K order: k = 4r+s (s<4), 20+r (s=4), 25..31 zero weights
+                uint8_t *dst = sm + OFF_IM + buf * IM_BYTES + m * 16;
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(A[0] ^ 0x80808080u, A[1] ^ 0x80808080u, A[2] ^ 0x80808080u, A[3] ^ 0x80808080u);
+                *reinterpret_cast<uint4 *>(dst + 128 * 16) = make_uint4(A[4] ^ 0x80808080u, bcol ^ 0x80808080u, b4 ^ 0x80u, 0u);
+            };
             int c3 = mod_pos(y0 - 4, 3);
             int c4_s1 = 0, c4_s2 = 0;
-            worker_bar();                                         // the workers' prologue barrier
+            // ---- prologue: input rows for a1 rows y0-4 and y0-3, C1 operand of the first ------------
+            for (int r = y0 - 6; r <= y0 - 1; ++r) store_in(r, load_in(r));
+            worker_bar();
+            im2col(y0 - 4, c3);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+            ++ev_work;
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
+                const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
+                // the C1 operand of the next iteration, stage (R1+1) mod 3: C1 of iteration i-2 (same stage) is complete,
+                // the workers saw its commit before the barrier that ended iteration i-1
+                if (i + 1 < niter) {
+                    if (!(EXP & 4)) im2col(R1 + 1, wrap_inc(c3, 3));
+                    fence_proxy_async_smem();                     // st.shared above -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+                    ++ev_work;
+                }
                 if (!(EXP & 1) && !(P.dbg_flags & 2) && i >= 3) {
                     const uint8_t *row = sm + OFF_A3 + c3 * A2_ROW + (7 + mo) * 16;      // slot (R1-9) mod 3 = R1 mod 3, pixel 7 + mo + dx
                     int acc[3] = {0, 0, 0};
@@ -521,7 +536,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         outf[(size_t)rowo * W + X0 + mo] = (uint8_t)residual_apply(u4 + P.c4_bias, x, P.c4_mul, P.c4_shift);   // cnn.cu:507-523
                     }
                 }
-                worker_bar();
+                store_in(R1 + 4, in_next);
+                worker_bar();                                     // input ring complete for the next im2col; a3 rows of the workers visible
             }
             worker_bar();                                         // the workers' drain barrier
         }
@@ -567,7 +583,7 @@ void build_mma_bases(uint32_t sb, uint32_t tm, PhaseBases *pb, FixedBases &fb)
         const int qa = wrap_sub(c6, 2, 6);                                            // (R1-2) mod 6
         PhaseBases &e = pb[ph];
         e = PhaseBases{};
-        e.im = sb + ((OFF_IM + par * IM_BYTES) >> 4) + ((128u * 16 >> 4) << 16);
+        e.im = sb + ((OFF_IM + c3 * IM_BYTES) >> 4) + ((128u * 16 >> 4) << 16);            // stage R1 mod 3
         e.a1_r2 = sb + (OFF_A1 >> 4) + wrap_sub(c3, 2, 3) * (A1_ROW >> 4) + LP;       // a1 row R1-2 (C2_2, C2_1)
         e.a2_r6 = sb + (OFF_A2 >> 4) + c3 * (A2_ROW >> 4);                            // a2 row R1-6 (C3_1, C3_2)
         e.b22 = w22 + (qa <= 2 ? 2 - qa : 8 - qa) * 16;                               // window start (8 - qa) mod 6 blocks of 16 rows
