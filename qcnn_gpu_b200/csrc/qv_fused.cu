@@ -58,6 +58,9 @@
 #ifndef QV_EXP
 #define QV_EXP 0
 #endif
+#ifndef QV_BIG_LAST
+#define QV_BIG_LAST 1
+#endif
 
 namespace qv {
 namespace {
@@ -297,6 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 MMA(KEEP, pb.z22, fb.zeroA, fb.w1, idesc_i8(128, 16), 0);        // C2_2 row R1
                 MMA(AGAIN, pb.z21, fb.zeroA, fb.w1, idesc_i8(128, 32), 0);       // C2_1 row R1-1
                 MMA(LAST, pb.z31, fb.zeroA, fb.w1, idesc_i8(128, 16), 0);        // C3_1 row R1-5
+                auto layer2 = [&]() {
                 // ---- layer 2: scatter a1 row R1-2.  C2_2 (5x5, 64 -> 16) into its 6-slot ring with N = 96, shifts
                 //      s = 0..4 (pixel 4+s) x K-halves h (planes 2h, 2h+1); C2_1 (3x3, 64 -> 32) into its 4-slot
                 //      ring with N = 128 reads the same tile for s = 1..3 and takes it from the collector ------------
@@ -311,6 +315,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         MMA(ONCE, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
                     }
                 }
+                };
+                if (!QV_BIG_LAST) layer2();
                 // ---- layer 3 on a2 row R1-6.  C3_1 (3x3, 48 -> 16) scatters into its 4-slot ring, N = 64; its K-steps
                 //      pair 16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights).
                 //      C3_2 (1x1, 48 -> 32, N = 32) needs exactly the tiles of K-steps 1 and 3 (centre pixel: planes 0,1
@@ -322,6 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 MMA(KEEP, fb.r31, pb.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, pb.b31 + 3 * (T31 >> 4), idesc_i8(128, 64), 1);
                 MMA(LAST, pb.d32, pb.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, fb.w32 + (T32 >> 4), idesc_i8(128, 32), 1);
                 MMA(ONCE, fb.r31, pb.a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, pb.b31 + 4 * (T31 >> 4), idesc_i8(128, 64), 1);
+                if (QV_BIG_LAST) layer2();      // experiment: the wide MMAs last leave the tensor pipe a backlog for the handshake
                 ph = wrap_inc(ph, N_PHASE);
                 pb_next = c_phase[ph];                            // three 16-byte constant loads, in flight during the handshake
                 if (leader) mma_commit(&bar_mma[ev_mma & 1]);
@@ -360,12 +367,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
             ++ev_work;
             int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
+            // image columns of this thread's a1 / a2 / a3 pixel inside the frame?  (each layer zero-pads its own input)
+            const bool xa1 = (unsigned)(X0 - 4 + m) < (unsigned)W, xa2 = (unsigned)(X0 - 2 + m) < (unsigned)W, xa3 = (unsigned)(X0 - 1 + m) < (unsigned)W;
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
                 if (PROF)
                     tr_slot = (P.dbg && unit == 0 && (tid == 0 || tid == 128) && i >= TR_ITER0 && i < TR_ITER0 + TR_N)
                                   ? (i - TR_ITER0) * 16 + 2 + (tid >> 7) * 4 : -1;
-                if (i >= 1 && (P.dbg_flags & 2)) {
+                if (PROF && i >= 1 && (P.dbg_flags & 2)) {           // experiment: wait, but drain nothing
                     warp_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1, lane, s_fail);
                     ++ev_mma;
                     fence_after_sync();
@@ -376,14 +385,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     fence_after_sync();
                     lap(0);
                     const uint32_t par = (R1p - 1) & 1;         // D1 / D32 stage the MMAs of iteration i-1 wrote
-                    const bool xa1 = X0 - 4 + m >= 0 && X0 - 4 + m < W, xa2 = X0 - 2 + m >= 0 && X0 - 2 + m < W, xa3 = X0 - 1 + m >= 0 && X0 - 1 + m < W;
-                    const bool v1 = R1 - 1 >= 0 && R1 - 1 < H && xa1;
+                    auto row_ok = [&](int r) { return (unsigned)r < (unsigned)H; };
+                    const bool v1 = row_ok(R1 - 1) && xa1;
                     uint8_t *dst1 = sm + OFF_A1 + wrap_sub(c3, 1, 3) * A1_ROW + (4 + m) * 16;
                     const uint32_t d1 = tm_lane + TM_D1 + par * 64;
                     uint32_t ra[16], rb[16], rc[16], rd[16], re[16];
                     if (hh == 0) {
-                        const bool v2 = R1 - 5 >= 0 && R1 - 5 < H && xa2, v2n = R1 - 4 >= 0 && R1 - 4 < H && xa2;
-                        const bool v3 = R1 - 8 >= 0 && R1 - 8 < H && xa3;
+                        const bool v2 = row_ok(R1 - 5) && xa2, v2n = row_ok(R1 - 4) && xa2, v3 = row_ok(R1 - 8) && xa3;
                         uint8_t *dst2 = sm + OFF_A2 + wrap_sub(c3, 5, 3) * A2_ROW + (6 + m) * 16;
                         uint8_t *dst2n = sm + OFF_A2 + wrap_sub(c3, 4, 3) * A2_ROW + (6 + m) * 16;
                         tmem_ld_x16(d1 + 0, ra); tmem_ld_x16(d1 + 16, rb);
@@ -397,8 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         requant_store<FAST, 80>(rd, P, P.q21, v2n, dst2n + 0 * PLANE);
                         if (!(EXP & 1)) requant_store<FAST, 112>(re, P, P.q31, v3, sm + OFF_A3 + wrap_sub(c3, 8, 3) * A2_ROW + (7 + m) * 16);   // a3 row R1-8 plane 0
                     } else {
-                        const bool v2n = R1 - 4 >= 0 && R1 - 4 < H && xa2;
-                        const bool v3n = R1 - 7 >= 0 && R1 - 7 < H && xa3;
+                        const bool v2n = row_ok(R1 - 4) && xa2, v3n = row_ok(R1 - 7) && xa3;
                         uint8_t *dst2n = sm + OFF_A2 + wrap_sub(c3, 4, 3) * A2_ROW + (6 + m) * 16;
                         const uint32_t d32 = tm_lane + TM_D32 + par * 32;
                         tmem_ld_x16(d1 + 32, ra); tmem_ld_x16(d1 + 48, rb);
