@@ -1,8 +1,9 @@
 // Fused QVRCNN forward for sm_100a: the whole network per column strip, activations resident in
-// shared memory, ALL six convolutions as tcgen05.mma kind::i8 implicit GEMMs with int32 accumulators
-// in TMEM; HBM sees one luma byte in and one reconstructed byte out per pixel.  Replaces, for one
-// frame batch, the whole of qvrcnn::forward_blu (inference/qvrcnn.cu:168-242): ppro, 6 x
-// (cudnnConvolutionForward + cudnnAddTensor), quantize_out_blu / concat_blu, applyRes_y.
+// shared memory, the five dense convolutions as tcgen05.mma kind::i8 implicit GEMMs with int32
+// accumulators in TMEM, the 48 -> 1 output layer on CUDA cores; HBM sees one luma byte in and one
+// reconstructed byte out per pixel.  Replaces, for one frame batch, the whole of qvrcnn::forward_blu
+// (inference/qvrcnn.cu:168-242): ppro, 6 x (cudnnConvolutionForward + cudnnAddTensor),
+// quantize_out_blu / concat_blu, applyRes_y.
 //
 // Geometry.  A CTA owns a work unit = (frame, column strip of WT=120 output pixels, row segment)
 // and rolls down the rows.  Every activation row lives in smem as [16-channel plane][pixel][16 B]
@@ -18,29 +19,36 @@
 // read once per horizontal shift and multiplied by the weights of ALL vertical taps at once:
 //   D[pixel, (out_row, k)] += A[in_row, pixel+s][c] * W[r = in_row - out_row + pad][s][c][k]
 // The accumulators of the output rows in flight form a ring in TMEM (slot = out_row mod ring
-// size); one MMA covers the whole ring, so N = 96 / 128 / 64 / 32.  The B operand for a ring of R
+// size); one MMA covers the whole ring, so N = 96 / 128 / 64.  The B operand for a ring of R
 // slots is stored as the block sequence [r_max .. r_0, Z] repeated (Z = zero block) and the
 // rotation that matches "slot = row mod R" is a start-address offset into it.  The slot of the
 // output row completed one step ago sits under the Z block (the MMA adds 0 to it) while the
 // workers drain it; the slot of the row that starts now is zeroed by one small MMA with a zero A.
 //
-// Shared-memory bandwidth is what binds this kernel (ncu: the smem data pipe is ~95 % busy, the tensor
-// core's operand fetches being 70 % of that), and 60 % of the tensor core's traffic is the A operand,
-// re-read by every MMA.  So MMAs that multiply the SAME activation tile are issued back to back and the
-// second takes A from the tensor core's collector (collector::a::fill -> ::lastuse): C2_2 shift s and
-// C2_1 shift s-1 read the same a1 tile, C3_1's centre-tap K-steps and C3_2's two K-steps read the same
+// Collector reuse.  60 % of the tensor core's shared-memory traffic is the A operand, re-read by every
+// MMA.  MMAs that multiply the SAME activation tile are therefore issued back to back and the second takes
+// A from the tensor core's collector (collector::a::fill -> ::lastuse, tools/umma_probe3.cu): C2_2 shift s
+// and C2_1 shift s-1 read the same a1 tile, C3_1's centre-tap K-steps and C3_2's two K-steps read the same
 // a2 tiles, and the three ring-slot initialisations share the zero tile.
 //
-// Pipeline.  9 warps: warps 0-7 are workers (TMEM -> requantise -> smem epilogues, im2col for C1,
-// C4 on CUDA cores, residual + store), warp 8 issues every MMA (one elected lane).  Iteration i,
-// R1 = y0-4+i:
-//   MMA side   : C1 for a1 row R1 (im2col operand); C2_2 and C2_1 scatter of a1 row R1-2; C3_1 scatter
-//                and C3_2 of a2 row R1-6
-//   worker side: drains what iteration i-1 completed: a1 row R1-1; a2 row R1-5 plane 2 (C2_2) and a2 row
-//                R1-4 planes 0,1 (C2_1); a3 row R1-8 channels 0-15 (C3_1) and a3 row R1-7 channels 16-47
-//                (C3_2), both only as C4 partial sums; output row R1-10 (+ residual, clamp, store);
-//                im2col for a1 row R1+1.
-// The two sides meet at two pairs of mbarriers per iteration.
+// Pipeline.  13 warps, three roles; iteration i, R1 = y0-4+i:
+//   warp 8, MMA issue : 27 MMAs per iteration -- C1 for a1 row R1 (im2col operand); the three ring-slot
+//                initialisations; C3_1 scatter and C3_2 of a2 row R1-6; C2_2 and C2_1 scatter of a1 row R1-2
+//                (the wide MMAs last: they execute slower than they issue, so the tensor pipe still has a
+//                backlog during the handshake).  Operand addresses come from a 12-phase table in constant
+//                memory (the ring rotations have periods 2, 3, 4, 6), prefetched one iteration ahead, plus
+//                uniform-datapath adds: the issue loop executes no ALU-pipe instruction, which matters because
+//                the worker warps of the same SM sub-partition saturate that pipe (profiles/r1_probe3_contention*).
+//   warps 0-7, workers: drain what iteration i-1 completed, TMEM -> requantise -> st.shared: a1 row R1-1; a2 row
+//                R1-5 plane 2 (C2_2) and a2 row R1-4 planes 0,1 (C2_1); a3 row R1-8 plane 0 (C3_1) and a3 row
+//                R1-7 planes 1,2 (C3_2).  A warp can only read its own TMEM lane quarter, so two warps share a
+//                quarter and split the ten 16-column groups five / five.
+//   warps 9-12, C4    : everything that needs no TMEM -- the input ring (global loads one row ahead), the C1
+//                operand of a1 row R1+1 (im2col, three stages), C4 on a3 row R1-9 (9 LDS.128 + 108 dp4a per
+//                pixel, two running sums carry the partial output rows), applyRes_y and the store of output row
+//                R1-10.
+// Workers and C4 warps arrive on one mbarrier pair that releases the next MMAs, the MMA warp commits to another
+// pair that releases the workers, and a named barrier per iteration publishes the a3 rows to the C4 warps.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
