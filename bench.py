@@ -292,7 +292,10 @@ def main():
         value = world * npx * args.steps / (total_ms * 1e-3) / 1e6
         per_gpu_px_s = npx * args.steps / (total_ms * 1e-3)
         tops = per_gpu_px_s * OPS_PER_PIXEL / 1e12
-        int8_peak = 2.0 * peaks["bf16_sustained"]
+        # int8 dense peak = 2 x the bf16 figure.  The kernel runs alone at the full SM clock (1965 MHz, ~310 W, no power
+        # throttling), so the BURST cuBLAS measurement is the denominator; the fraction of the sustained (power-capped,
+        # ~1.36 GHz) figure and of the nominal 4.5 POP/s are reported beside it.
+        int8_peak = 2.0 * peaks["bf16_burst"]
         line = {
             "metric": "luma Mpixel/s (QVRCNN int8, 1080p)", "value": value, "unit": "Mpixel/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -303,8 +306,8 @@ def main():
             "e2e": {"value": e2e_mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": npx, "d2h_bytes_per_step": npx,
                     "api": "qv_forward_frames_host (pinned host in/out)", "bit_identical_to_device_path": same},
             "roofline": {"bound": "tensor", "achieved": tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": tops / int8_peak,
-                         "traffic": ncu_traffic(), "peak_source": "2 x bf16_tflops_sustained, " + peaks["source"],
-                         "frac_of_2x_bf16_burst": tops / (2.0 * peaks["bf16_burst"]), "frac_of_nominal_4500": tops / 4500.0,
+                         "traffic": ncu_traffic(), "peak_source": "2 x bf16_tflops (burst), " + peaks["source"],
+                         "frac_of_2x_bf16_sustained": tops / (2.0 * peaks["bf16_sustained"]), "frac_of_nominal_4500": tops / 4500.0,
                          "hbm": {"achieved_gbs": per_gpu_px_s * HBM_BYTES_PER_PIXEL / 1e9, "peak_gbs": peaks["hbm_gbs"],
                                  "frac": per_gpu_px_s * HBM_BYTES_PER_PIXEL / 1e9 / peaks["hbm_gbs"]},
                          "kernel_ms_per_launch": total_ms / max(1, launches)},
