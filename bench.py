@@ -242,7 +242,10 @@ def main():
         net.forward_frames_device(d_in.data_ptr(), d_out.data_ptr(), FRAMES, stream.cuda_stream)
 
     sampler = ClockSampler(local)
-    sampler.start()                              # comes up during the warm-up; its samples are cleared below
+    sampler.start()
+    t_s = time.perf_counter()
+    while not sampler.samples and time.perf_counter() - t_s < 8.0:      # nvidia-smi takes a second or two to come up:
+        time.sleep(0.05)                                                 # the timed region must not be over before it does
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
