@@ -215,6 +215,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    from qcnn_gpu_b200.host import numa
+    # host threads + pinned staging on the GPU's NUMA node: matters for e2e when N ranks share the host; at N = 1 the
+    # process keeps all cores (the cpu_baseline leg uses them)
+    numa_info = numa.bind_to_gpu(local) if world > 1 else {"bound": False}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -307,7 +311,8 @@ def main():
                        "l2": "inputs+outputs (265 MB/step) larger than L2 (126 MB)"},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": npx, "d2h_bytes_per_step": npx,
-                    "api": "qv_forward_frames_host (pinned host in/out)", "bit_identical_to_device_path": same},
+                    "api": "qv_forward_frames_host (pinned host in/out)", "bit_identical_to_device_path": same,
+                    "numa": numa_info},
             "roofline": {"bound": "tensor", "achieved": tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": tops / int8_peak,
                          "traffic": ncu_traffic(), "peak_source": "2 x bf16_tflops (burst), " + peaks["source"],
                          "frac_of_2x_bf16_sustained": tops / (2.0 * peaks["bf16_sustained"]), "frac_of_nominal_4500": tops / 4500.0,
