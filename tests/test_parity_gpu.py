@@ -149,6 +149,47 @@ def test_fused_equals_layered_1080p(models):
     assert np.array_equal(out_f[0], _oracle(m).forward_blu(anchor[0:1])[0])
 
 
+def test_full_size_properties_4k_and_8k(models):
+    """BASELINE configs 4 and 5 at their real frame sizes, through properties that need no CPU oracle run:
+    (a) 3840x2160, QP 27: frames are independent -- a frame inside a batch of 3 equals the same frame processed alone,
+        a permuted batch gives the permuted output, and the two CUDA implementations agree;
+    (b) 7680x4320, QP 22: fused == layered on the whole frame, and a 1300x2100 window with a 6-pixel margin reproduces
+        the frame's interior (the net is a stencil of radius 6: SURVEY 8e);
+    (c) the oracle pins one 64-row band of the 4K frame (rows 1000..1063 with their halo)."""
+    m4, m8 = models[27], models[22]
+    # (a)
+    h, w = 2160, 3840
+    anchor, _ = synth.make_frames(0xC0FFEE + 9, 3, h, w)
+    net = _net(m4, 3, h, w, api.IMPL_LAYERED)
+    out_l = net.forward_frames_host(anchor)
+    _fused_or_skip(net, api.IMPL_FUSED)
+    net.set_impl(api.IMPL_FUSED)
+    out_f = net.forward_frames_host(anchor)
+    assert np.array_equal(out_l, out_f)
+    perm = anchor[[2, 0, 1]]
+    assert np.array_equal(net.forward_frames_host(perm), out_f[[2, 0, 1]])
+    one = _net(m4, 1, h, w, api.IMPL_FUSED)
+    assert np.array_equal(one.forward_frames_host(anchor[1:2])[0], out_f[1])
+    # (c) oracle on a band: rows 994..1069 as a frame; its rows 6..69 are exact for the 4K frame's rows 1000..1063
+    band = np.ascontiguousarray(anchor[0:1, 994:1070, :])
+    want = _oracle(m4).forward_blu(band)[0][6:70]
+    assert np.array_equal(out_f[0][1000:1064], want)
+    del net, one
+    # (b)
+    h, w = 4320, 7680
+    anchor, _ = synth.make_frames(0xC0FFEE + 10, 1, h, w)
+    net = _net(m8, 1, h, w, api.IMPL_LAYERED)
+    out_l = net.forward_frames_host(anchor)
+    net.set_impl(api.IMPL_FUSED)
+    out_f = net.forward_frames_host(anchor)
+    assert np.array_equal(out_l, out_f)
+    y0, x0, hh, ww = 1501, 2999, 1300, 2100
+    win = np.ascontiguousarray(anchor[:, y0:y0 + hh, x0:x0 + ww])
+    wnet = _net(m8, 1, hh, ww, api.IMPL_FUSED)
+    out_w = wnet.forward_frames_host(win)[0]
+    assert np.array_equal(out_w[6:-6, 6:-6], out_f[0][y0 + 6:y0 + hh - 6, x0 + 6:x0 + ww - 6])
+
+
 @pytest.mark.parametrize("impl", IMPLS, ids=lambda i: IMPL_NAME[i])
 def test_rows_mode_strips_equal_whole_frame(models, impl):
     """Spatial partition (BASELINE config 5 in miniature): a frame cut into 3 horizontal strips with
