@@ -314,6 +314,16 @@ int qv_load_data(qv_net *net, const uint8_t *host_luma)
     return QV_OK;
 }
 
+// After a synchronisation: did a CTA of the fused kernel report a failure?  (Never a silent wrong answer.)
+static int kernel_report(qv_net *net)
+{
+    const int f = net->fm ? fused_take_failure(net->fm) : 0;
+    if (!f) return QV_OK;
+    set_error(f == 2 ? "fused kernel: a CTA saw other shared-memory / TMEM bases than the operand table was built for"
+                     : "fused kernel: an mbarrier wait timed out (the frame data of this call is not valid)");
+    return QV_ERR_CUDA;
+}
+
 int qv_forward_blu(qv_net *net)
 {
     if (!net) { set_error("qv_forward_blu: null handle"); return QV_ERR_ARG; }
@@ -322,7 +332,7 @@ int qv_forward_blu(qv_net *net)
     rc = run_forward(net, net->d_x, net->d_rec, net->batch, net->H, net->W, net->st);
     if (rc) return rc;
     QV_CUDA(cudaStreamSynchronize(net->st));        // the reference is synchronous (kernel.cu:95)
-    return QV_OK;
+    return kernel_report(net);
 }
 
 int qv_get_recon(qv_net *net, uint8_t *host_out)
@@ -333,7 +343,7 @@ int qv_get_recon(qv_net *net, uint8_t *host_out)
     const size_t bytes = (size_t)net->batch * net->H * net->W;
     QV_CUDA(cudaMemcpyAsync(host_out, net->d_rec, bytes, cudaMemcpyDeviceToHost, net->st));   // kernel.cu:96
     QV_CUDA(cudaStreamSynchronize(net->st));
-    return QV_OK;
+    return kernel_report(net);
 }
 
 int qv_forward_frames_device(qv_net *net, const uint8_t *d_in, uint8_t *d_out, int n_frames, void *cuda_stream)
@@ -346,7 +356,7 @@ int qv_forward_frames_device(qv_net *net, const uint8_t *d_in, uint8_t *d_out, i
         rc = run_forward(net, d_in, d_out, n_frames, net->H, net->W, st);
         if (rc) return rc;
     }
-    if (!cuda_stream) QV_CUDA(cudaStreamSynchronize(st));
+    if (!cuda_stream) { QV_CUDA(cudaStreamSynchronize(st)); return kernel_report(net); }
     return QV_OK;
 }
 
@@ -458,7 +468,7 @@ int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int
     }
     if ((rc = drain(0))) return rc;
     if ((rc = drain(1))) return rc;
-    return QV_OK;
+    return kernel_report(net);
 }
 
 int qv_device_buffers(qv_net *net, void **d_x, void **d_x_rec)

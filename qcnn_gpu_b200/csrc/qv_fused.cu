@@ -133,7 +133,8 @@ struct FusedParams {
     int c4_bias, c4_mul, c4_shift;
     int c4_w[108];                     // C4 weights [tap][plane][4 words], 4 channels per word (CUDA-core dp4a)
     long long *dbg;                    // optional per-block phase timers (QV_FUSED_PROFILE=1), else null
-    uint32_t sbase16, tmem_base;       // what c_mma was built for (checked by the kernel)
+    uint32_t sbase16, tmem_base;       // what the operand table was built for (checked by the kernel)
+    int *fail_flag;                    // mapped host memory: a CTA that detects a failure reports it here
     int dbg_flags;                     // tuning experiments only (QV_FUSED_EXPERIMENT): 1 = issue no MMAs, 2 = workers skip the drains
     int bias[BIAS_INTS];               // per accumulator column: layer bias (+ rounding bias on the FAST path)
 };
@@ -560,6 +561,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     fence_before_sync();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tm, TM_COLS);
+    if (tid == 0 && *s_fail) {
+        *reinterpret_cast<volatile int *>(P.fail_flag) = *s_fail;
+        __threadfence_system();
+    }
     if (tid == 0 && *s_fail)
         printf(*s_fail == 2 ? "qv fused kernel: block %d has other shared-memory / TMEM bases than the descriptor table was built for\n"
                             : "qv fused kernel: mbarrier wait timed out in block %d\n", blockIdx.x);
@@ -615,6 +620,7 @@ void build_mma_bases(uint32_t sb, uint32_t tm, PhaseBases *pb, FixedBases &fb)
 
 // =================================== host side ==========================================
 struct FusedModel {
+    int *h_fail = nullptr;             // cudaHostAlloc'ed, mapped: kernel failure report
     uint8_t *d_wimg = nullptr;
     FusedParams proto{};
     bool fast = true;
@@ -767,14 +773,35 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     }
     fm->sm_count = sms;
     P.wimg = fm->d_wimg;
+    P.fail_flag = nullptr;
+    if (cudaHostAlloc(&fm->h_fail, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+        *fm->h_fail = 0;
+        if (cudaHostGetDevicePointer(&P.fail_flag, fm->h_fail, 0) != cudaSuccess) P.fail_flag = nullptr;
+    }
+    if (!P.fail_flag) {
+        set_error("fused_upload: no mapped host memory for the failure report");
+        if (fm->h_fail) cudaFreeHost(fm->h_fail);
+        cudaFree(fm->d_wimg);
+        delete fm;
+        return nullptr;
+    }
     return fm;
 }
 
 void fused_free(FusedModel *fm)
 {
     if (!fm) return;
+    if (fm->h_fail) cudaFreeHost(fm->h_fail);
     cudaFree(fm->d_wimg);
     delete fm;
+}
+
+int fused_take_failure(const FusedModel *fm)
+{
+    if (!fm || !fm->h_fail) return 0;
+    const int f = *reinterpret_cast<volatile int *>(fm->h_fail);
+    if (f) *fm->h_fail = 0;
+    return f;
 }
 
 cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_out, int n, int H, int W, cudaStream_t st,
@@ -808,6 +835,7 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     const bool prof = getenv("QV_FUSED_PROFILE") != nullptr;
     P.dbg = nullptr;
     P.dbg_flags = getenv("QV_FUSED_EXPERIMENT") ? atoi(getenv("QV_FUSED_EXPERIMENT")) : 0;
+    if (getenv("QV_FUSED_TEST_FAIL")) P.sbase16 ^= 1u;        // tests only: make every CTA report a base mismatch
     const size_t dbg_n = (size_t)grid * 16 + TR_N * 48;
     if (prof && cudaMalloc(&P.dbg, dbg_n * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
     if (P.dbg) cudaMemsetAsync(P.dbg, 0, dbg_n * sizeof(long long), st);

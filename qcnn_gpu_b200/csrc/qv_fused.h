@@ -15,5 +15,8 @@ void fused_free(FusedModel *fm);
 // Whole net on n frames of HxW luma resident in device memory, one launch.
 cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_out, int n, int H, int W,
                           cudaStream_t st, long long *launches);
+// After the stream the kernel ran on has been synchronised: 0, or what a CTA reported (1 = an mbarrier wait timed
+// out, 2 = shared-memory / TMEM bases other than the operand table was built for); the report is cleared.
+int fused_take_failure(const FusedModel *fm);
 
 }  // namespace qv

@@ -262,6 +262,22 @@ def test_error_behaviour(models, tmp_path):
     assert e.value.code == -4
 
 
+def test_kernel_failure_is_reported(models, monkeypatch):
+    """A CTA of the fused kernel that detects a problem (here: forced, the operand-table check) must surface as an
+    error code of the call that synchronises -- never as a silently wrong frame."""
+    net = _net(models[32], 1, 64, 250, api.IMPL_LAYERED)
+    _fused_or_skip(net, api.IMPL_FUSED)
+    net.set_impl(api.IMPL_FUSED)
+    x = np.full((1, 64, 250), 77, np.uint8)
+    net.load_data(x)
+    monkeypatch.setenv("QV_FUSED_TEST_FAIL", "1")
+    with pytest.raises(api.QVError, match="operand table"):
+        net.forward_blu()
+    monkeypatch.delenv("QV_FUSED_TEST_FAIL")
+    net.forward_blu()                                   # the report was consumed; the handle keeps working
+    assert np.array_equal(net.get_recon(), _oracle(models[32]).forward_blu(x))
+
+
 def test_quant_param_file_plus_set_weights(models, tmp_path):
     """The shipped artefact is the per-QP scale file; weights come separately."""
     m = models[27]
