@@ -4,6 +4,7 @@
 // inference/qvrcnn.cu:4-68,168-242) and the hot loop of testqvrcnn (inference/kernel.cu:86-97).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -405,18 +406,29 @@ int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int
     const size_t fpx = (size_t)net->H * net->W;
     // Pipeline granularity: the H2D of chunk k+1 and the D2H of chunk k-1 hide behind the compute of chunk k;
     // only the first upload and the last download are exposed, so the schedule is tapered -- small chunks at
-    // both ends (1/16, 3/16, 1/4, 1/4, 3/16, 1/16 of the frames), each at most `batch` frames.
+    // both ends (1, 3, 4, 8, 16, 16, 8, 4, 3, 1 sixty-fourths of the frames; measured best of seven schedules at
+    // 64 x 1080p, profiles/r1_e2e_chunk_schedules.log), each at most `batch` frames.
     std::vector<int> chunks;
     {
-        static const int num[6] = {1, 3, 4, 4, 3, 1};
+        static const int num[10] = {1, 3, 4, 8, 16, 16, 8, 4, 3, 1};
         int left = n_frames;
         if (n_frames >= 16) {
-            for (int k = 0; k < 6 && left > 0; ++k) {
-                int want = k == 5 ? left : std::max(1, n_frames * num[k] / 16);
+            for (int k = 0; k < 10 && left > 0; ++k) {
+                int want = k == 9 ? left : std::max(1, n_frames * num[k] / 64);
                 while (want > 0 && left > 0) {
                     const int c = std::min(std::min(want, left), net->batch);
                     chunks.push_back(c); want -= c; left -= c;
                 }
+            }
+        }
+        const char *ov = getenv("QV_E2E_CHUNKS");                  // tuning only: explicit chunk sizes, e.g. "4,4,8,16,16,8,4,4"
+        if (ov && *ov) {
+            chunks.clear(); left = n_frames;
+            for (const char *p = ov; *p && left > 0;) {
+                const int c = std::min(std::min(std::max(1, atoi(p)), left), net->batch);
+                chunks.push_back(c); left -= c;
+                while (*p && *p != ',') ++p;
+                if (*p == ',') ++p;
             }
         }
         const int uni = std::max(1, std::min(net->batch, (n_frames + 3) / 4));
@@ -456,9 +468,11 @@ int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int
         const uint8_t *src = h_in + (size_t)f0 * fpx;
         if (!pinned_in) { memcpy(net->h_pin_in[slot], src, bytes); src = net->h_pin_in[slot]; }
         QV_CUDA(cudaMemcpyAsync(net->d_slot_in[slot], src, bytes, cudaMemcpyHostToDevice, net->pst[slot]));
-        // compute stages run one after the other (they share the handle's scratch and every SM anyway);
-        // only the copies of one slot overlap the compute of the other
-        if (f0 > 0) QV_CUDA(cudaStreamWaitEvent(net->pst[slot], net->ev_compute, 0));
+        // The layered path's compute stages must run one after the other (they share the handle's activation scratch).
+        // The fused kernel has no scratch: its launches of the two slots are left unordered, so the persistent CTAs of the
+        // next chunk move onto the SMs the previous chunk's last wave has already left.
+        const bool fused_path = net->impl == QV_IMPL_FUSED || (net->impl == QV_IMPL_AUTO && net->fm);
+        if (f0 > 0 && !fused_path) QV_CUDA(cudaStreamWaitEvent(net->pst[slot], net->ev_compute, 0));
         rc = run_forward(net, net->d_slot_in[slot], net->d_slot_out[slot], c, net->H, net->W, net->pst[slot]);
         if (rc) return rc;
         QV_CUDA(cudaEventRecord(net->ev_compute, net->pst[slot]));
