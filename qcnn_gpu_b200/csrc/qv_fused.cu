@@ -66,9 +66,6 @@
 #ifndef QV_EXP
 #define QV_EXP 0
 #endif
-#ifndef QV_BIG_LAST
-#define QV_BIG_LAST 1
-#endif
 
 namespace qv {
 namespace {
@@ -303,29 +300,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 0] = tc0;
                     stamp = tr ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
                 }
-                // ---- C1: a1 row R1 = im2col[R1 & 1] x W1 (N = 64) --------------------------------------
+                // ---- C1: a1 row R1 = im2col stage (R1 mod 3) x W1 (N = 64) -------------------------------
                 MMA(ONCE, pb.d1, pb.im, fb.w1, idesc_i8(128, 64), 0);
                 // ---- the ring slots of the rows that start in this iteration: 0 = zero tile x anything ------
                 MMA(KEEP, pb.z22, fb.zeroA, fb.w1, idesc_i8(128, 16), 0);        // C2_2 row R1
                 MMA(AGAIN, pb.z21, fb.zeroA, fb.w1, idesc_i8(128, 32), 0);       // C2_1 row R1-1
                 MMA(LAST, pb.z31, fb.zeroA, fb.w1, idesc_i8(128, 16), 0);        // C3_1 row R1-5
-                auto layer2 = [&]() {
-                // ---- layer 2: scatter a1 row R1-2.  C2_2 (5x5, 64 -> 16) into its 6-slot ring with N = 96, shifts
-                //      s = 0..4 (pixel 4+s) x K-halves h (planes 2h, 2h+1); C2_1 (3x3, 64 -> 32) into its 4-slot
-                //      ring with N = 128 reads the same tile for s = 1..3 and takes it from the collector ------------
-#pragma unroll
-                for (int t = 0; t < 10; ++t) {
-                    const int s = t / 2, h = t & 1;
-                    const uint32_t a = pb.a1_r2 + ((h * 2 * PLANE + (4 + s) * 16) >> 4);
-                    if (s >= 1 && s <= 3) {
-                        MMA(KEEP, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
-                        MMA(LAST, fb.r21, a, pb.b21 + ((s - 1) * 2 + h) * (T21 >> 4), idesc_i8(128, 128), 1);
-                    } else {
-                        MMA(ONCE, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
-                    }
-                }
-                };
-                if (!QV_BIG_LAST) layer2();
                 // ---- layer 3 on a2 row R1-6.  C3_1 (3x3, 48 -> 16) scatters into its 4-slot ring, N = 64; its K-steps
                 //      pair 16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights).
                 //      C3_2 (1x1, 48 -> 32, N = 32) needs exactly the tiles of K-steps 1 and 3 (centre pixel: planes 0,1
@@ -337,7 +317,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 MMA(KEEP, fb.r31, pb.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, pb.b31 + 3 * (T31 >> 4), idesc_i8(128, 64), 1);
                 MMA(LAST, pb.d32, pb.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, fb.w32 + (T32 >> 4), idesc_i8(128, 32), 1);
                 MMA(ONCE, fb.r31, pb.a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, pb.b31 + 4 * (T31 >> 4), idesc_i8(128, 64), 1);
-                if (QV_BIG_LAST) layer2();      // experiment: the wide MMAs last leave the tensor pipe a backlog for the handshake
+                // ---- layer 2: scatter a1 row R1-2.  C2_2 (5x5, 64 -> 16) into its 6-slot ring with N = 96, shifts
+                //      s = 0..4 (pixel 4+s) x K-halves h (planes 2h, 2h+1); C2_1 (3x3, 64 -> 32) into its 4-slot
+                //      ring with N = 128 reads the same tile for s = 1..3 and takes it from the collector.  Issued last: these
+                //      MMAs execute slower than they issue, so the tensor pipe has a backlog to work on during the handshake ---
+#pragma unroll
+                for (int t = 0; t < 10; ++t) {
+                    const int s = t / 2, h = t & 1;
+                    const uint32_t a = pb.a1_r2 + ((h * 2 * PLANE + (4 + s) * 16) >> 4);
+                    if (s >= 1 && s <= 3) {
+                        MMA(KEEP, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
+                        MMA(LAST, fb.r21, a, pb.b21 + ((s - 1) * 2 + h) * (T21 >> 4), idesc_i8(128, 128), 1);
+                    } else {
+                        MMA(ONCE, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
+                    }
+                }
                 ph = wrap_inc(ph, N_PHASE);
                 pb_next = c_phase[ph];                            // three 16-byte constant loads, in flight during the handshake
                 if (leader) mma_commit(&bar_mma[ev_mma & 1]);
@@ -853,10 +847,10 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
         for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
         const double iters = (double)P.n_units / grid * (P.seg_rows + PIPE);
         fprintf(stderr, "[qv fused profile] units=%d grid=%d iters/block~%.0f | cycles per iteration: MMA warp wait=%.0f issue=%.0f | "
-                "worker w0: wait_mma=%.0f drain(a1,a2)=%.0f (of which tcgen05.ld+wait %.0f) im2col+arrive=%.0f a3+c4=%.0f bar=%.0f | "
-                "worker w4: wait_mma=%.0f drain(a1,a2)=%.0f (tcgen05.ld+wait %.0f) im2col+arrive=%.0f a3+c4=%.0f bar=%.0f\n",
-                P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[14] / iters, a[4] / iters, a[6] / iters, a[5] / iters,
-                a[8] / iters, a[9] / iters, a[15] / iters, a[10] / iters, a[12] / iters, a[11] / iters);
+                "worker w0: wait_mma=%.0f drain=%.0f (of which tcgen05.ld+wait %.0f) fence+arrive=%.0f bar=%.0f | "
+                "worker w4: wait_mma=%.0f drain=%.0f (tcgen05.ld+wait %.0f) fence+arrive=%.0f bar=%.0f\n",
+                P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[14] / iters, a[4] / iters, a[5] / iters,
+                a[8] / iters, a[9] / iters, a[15] / iters, a[10] / iters, a[11] / iters);
         // timeline of block 0: per traced iteration, cycles relative to the first issue start
         const long long *tr = h.data() + (size_t)grid * 16, t0 = tr[0];
         if (t0)
