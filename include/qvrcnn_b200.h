@@ -106,6 +106,16 @@ QV_API int qv_get_recon(qv_net *net, uint8_t *host_out);
    sync, D2H) over n_frames host frames, pipelined: pinned staging, H2D / compute / D2H
    overlapped on private streams, `batch` frames per chunk.  h_in / h_out may be pageable. */
 QV_API int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int n_frames);
+/* The whole of testqvrcnn's data path for sequences that need not fit in host memory: frames
+   [first_frame, first_frame + n_frames) of the anchor YUV 4:2:0 file are read chunk by chunk into pinned
+   buffers by a reader thread (luma only, file stride h*w*3/2: inference/yuv_data.cpp:32-38), uploaded,
+   enhanced, downloaded and written by a writer thread into `recon_yuv` in save_recon_as' layout (Y plane +
+   h*w/2 zero bytes per frame, inference/yuv_data.cpp:119-125, at the frame's own offset) -- file reads,
+   copies, compute and file writes of different chunks overlap.  With `ori_yuv` the exact integer SSE of the
+   anchor and of the reconstruction against the original are accumulated on the device (the integer core of
+   vrcnn_data::psnr, inference/yuv_data.cpp:87-97).  ori_yuv, recon_yuv, sse_before, sse_after may be NULL. */
+QV_API int qv_stream_yuv(qv_net *net, const char *anchor_yuv, const char *ori_yuv, const char *recon_yuv,
+                         int first_frame, int n_frames, int64_t *sse_before, int64_t *sse_after);
 /* Same pass on frames already resident in device memory (n_frames may exceed `batch`);
    asynchronous on `cuda_stream` (a cudaStream_t, NULL = the handle's own stream, in which
    case the call synchronises before returning). */

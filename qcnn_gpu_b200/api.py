@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "qv_last_error", "qv_version", "qv_create", "qv_destroy", "qv_load_static_para",
     "qv_load_static_para_mem", "qv_load_static_para_hwcn", "qv_load_quant_params", "qv_read_quant_params",
     "qv_set_weights", "qv_get_quant_params", "qv_load_data", "qv_forward_blu", "qv_get_recon",
-    "qv_forward_frames_host", "qv_forward_frames_device", "qv_forward_rows_device", "qv_device_buffers",
+    "qv_forward_frames_host", "qv_stream_yuv", "qv_forward_frames_device", "qv_forward_rows_device", "qv_device_buffers",
     "qv_sse_device",
     "qv_set_impl", "qv_get_impl", "qv_launch_count", "qv_get_activation",
     "qv_convert_model_hwcn_to_vect_c", "qv_yuv_read_luma", "qv_yuv_read_frame", "qv_yuv_write_recon",
@@ -68,6 +68,7 @@ def lib():
         L.qv_get_recon.argtypes = [vp, vp]
         L.qv_forward_frames_host.argtypes = [vp, vp, vp, i32]
         L.qv_forward_frames_device.argtypes = [vp, vp, vp, i32, vp]
+        L.qv_stream_yuv.argtypes = [vp, cp, cp, cp, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.qv_forward_rows_device.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
         L.qv_sse_device.argtypes = [vp, vp, C.c_size_t, vp, vp]
         L.qv_set_impl.argtypes = [vp, i32]
@@ -166,6 +167,14 @@ class QVRCNN:
             out = np.empty_like(x)
         _check(lib().qv_forward_frames_host(self._h, x.ctypes.data, out.ctypes.data, n))
         return out
+
+    def stream_yuv(self, anchor_yuv: str, ori_yuv: Optional[str], recon_yuv: Optional[str], first_frame: int, n_frames: int):
+        """Files in, file out, overlapped (qv_stream_yuv); returns (sse_before, sse_after) -- zeros without `ori_yuv`."""
+        b, a = C.c_int64(0), C.c_int64(0)
+        enc = lambda p: p.encode() if p else None
+        _check(lib().qv_stream_yuv(self._h, enc(anchor_yuv), enc(ori_yuv), enc(recon_yuv), first_frame, n_frames,
+                                   C.byref(b) if ori_yuv else None, C.byref(a) if ori_yuv else None))
+        return int(b.value), int(a.value)
 
     def forward_frames_host_ptr(self, in_ptr: int, out_ptr: int, n: int) -> None:
         _check(lib().qv_forward_frames_host(self._h, in_ptr, out_ptr, n))

@@ -8,6 +8,8 @@
 //   --gpus <n>   frame-sharded over n devices, one host thread per device (no communication;
 //                the exact int64 SSE partial sums are added on the host)
 //   --save-recon <file>
+//   --stream     files in, file out through qv_stream_yuv: the sequence is never held in host memory (reader thread,
+//                GPU stage and writer thread overlap); PSNR from the exact on-device SSE
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -26,6 +28,7 @@ struct Options {
     std::vector<int> qps{22};
     int frames = 1, gpus = 1;
     std::string save_recon;
+    bool stream = false;
 };
 
 static void testqvrcnn(const char *ori_fn, const char *input_fn, const char *model_fn, int frame, int channel, int height,
@@ -81,13 +84,70 @@ static void testqvrcnn(const char *ori_fn, const char *input_fn, const char *mod
     else { fwrite(&psnr2, sizeof(double), 1, logfile); fclose(logfile); }
 }
 
+// --stream: the same report from the streaming pipeline.  Each GPU takes a contiguous frame range and fills its own part
+// of the reconstruction file; the SSE partial sums are exact integers, so their sum is the sequential result.
+static void testqvrcnn_stream(const char *ori_fn, const char *input_fn, const char *model_fn, int frame, int channel, int height,
+                              int width, const Options &opt)
+{
+    const int G = opt.gpus;
+    const size_t fpx = (size_t)channel * height * width;
+    std::vector<qv_net *> nets(G, nullptr);
+    for (int g = 0; g < G; ++g) {
+        if (qv_create(g, std::min(std::max(frame / G, 1), 8), channel, height, width, &nets[g]) || qv_load_static_para(nets[g], model_fn)) {
+            printf("%s\n", qv_last_error());
+            exit(1);
+        }
+    }
+    std::vector<long long> sb(G, 0), sa(G, 0);
+    std::vector<int> rcs(G, 0);
+    auto t0 = std::chrono::steady_clock::now();
+    {
+        std::vector<std::thread> th;
+        int f0 = 0;
+        for (int g = 0; g < G; ++g) {
+            const int nf = frame / G + (g < frame % G ? 1 : 0);
+            th.emplace_back([&, g, f0, nf] {
+                int64_t b = 0, a = 0;
+                rcs[g] = qv_stream_yuv(nets[g], input_fn, ori_fn, opt.save_recon.empty() ? nullptr : opt.save_recon.c_str(), f0, nf, &b, &a);
+                sb[g] = b; sa[g] = a;
+            });
+            f0 += nf;
+        }
+        for (auto &t : th) t.join();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    const long long us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    long long b = 0, a = 0;
+    for (int g = 0; g < G; ++g) {
+        if (rcs[g]) { printf("%s\n", qv_last_error()); exit(1); }
+        b += sb[g]; a += sa[g];
+        qv_destroy(nets[g]);
+    }
+    const double psnr1 = qv_psnr_from_sse(b, (size_t)frame * fpx), psnr2 = qv_psnr_from_sse(a, (size_t)frame * fpx);
+    time_t now = time(0);
+    printf("\nbefore net:PSNR=%.3f\nafter quantized net:PSNR=%.3f\ntime:%lldus\n", psnr1, psnr2, us);
+    printf("throughput:%.1f Mpixel/s (%d frame(s) of %dx%d on %d GPU(s), streamed from and to files)\n",
+           (double)frame * fpx / (double)us, frame, width, height, G);
+    FILE *logfile = fopen("log.txt", "a+");
+    if (!logfile) printf("write file failed\n");
+    else {
+        fprintf(logfile, "\nQVRCNN test date:%sdata:%s\nframes:%d\nheight:%d\nwidth:%d\nbefore net:PSNR=%f\nafter quantized net:PSNR=%f\ntime:%lldus\n",
+                ctime(&now), input_fn, frame, height, width, psnr1, psnr2, us);
+        fclose(logfile);
+    }
+    logfile = fopen("recon_psnr.data", "ab+");
+    if (!logfile) printf("open psnr file failed\n");
+    else { fwrite(&psnr2, sizeof(double), 1, logfile); fclose(logfile); }
+}
+
 static int run_all(const char *oriname, const char *inputname, int height, int width, const Options &opt)
 {
     for (int qp : opt.qps) {
         char input_fn[512], model_fn[512];
         snprintf(input_fn, sizeof(input_fn), "%sQ%d.yuv", inputname, qp);           // kernel.cu:124
         snprintf(model_fn, sizeof(model_fn), opt.model_tmpl.c_str(), qp);           // kernel.cu:125
-        testqvrcnn(oriname, input_fn, model_fn, opt.frames, 1, height, width, opt);
+        if (opt.stream) testqvrcnn_stream(oriname, input_fn, model_fn, opt.frames, 1, height, width, opt);
+        else testqvrcnn(oriname, input_fn, model_fn, opt.frames, 1, height, width, opt);
     }
     return 0;
 }
@@ -95,7 +155,7 @@ static int run_all(const char *oriname, const char *inputname, int height, int w
 int main(int argc, char **argv)
 {
     if (argc < 5) {
-        fprintf(stderr, "usage: %s <ori.yuv> <anchor_prefix> <H> <W> [--model tmpl%%d] [--qp 22,27,..] [--frames n] [--gpus n] [--save-recon f]\n", argv[0]);
+        fprintf(stderr, "usage: %s <ori.yuv> <anchor_prefix> <H> <W> [--model tmpl%%d] [--qp 22,27,..] [--frames n] [--gpus n] [--save-recon f] [--stream]\n", argv[0]);
         return 2;
     }
     Options opt;
@@ -105,6 +165,7 @@ int main(int argc, char **argv)
         else if (a == "--frames" && i + 1 < argc) opt.frames = atoi(argv[++i]);
         else if (a == "--gpus" && i + 1 < argc) opt.gpus = atoi(argv[++i]);
         else if (a == "--save-recon" && i + 1 < argc) opt.save_recon = argv[++i];
+        else if (a == "--stream") opt.stream = true;
         else if (a == "--qp" && i + 1 < argc) {
             opt.qps.clear();
             for (char *t = strtok(argv[++i], ","); t; t = strtok(nullptr, ",")) opt.qps.push_back(atoi(t));

@@ -3,9 +3,12 @@
 // variants the multi-GPU driver uses.  Mirrors class qvrcnn (inference/qvrcnn.cuh:25-59,
 // inference/qvrcnn.cu:4-68,168-242) and the hot loop of testqvrcnn (inference/kernel.cu:86-97).
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -482,6 +485,165 @@ int qv_forward_frames_host(qv_net *net, const uint8_t *h_in, uint8_t *h_out, int
     }
     if ((rc = drain(0))) return rc;
     if ((rc = drain(1))) return rc;
+    return kernel_report(net);
+}
+
+// ---- streaming file pipeline -------------------------------------------------------------
+namespace {
+struct StreamSlot {
+    uint8_t *h_in = nullptr, *h_ori = nullptr, *h_out = nullptr;      // pinned
+    uint8_t *d_in = nullptr, *d_ori = nullptr, *d_out = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    int state = 0;                       // 0 free -> 1 filled by the reader -> 2 launched -> 0 (written)
+    int f0 = 0, c = 0;
+};
+struct StreamShared {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool failed = false;
+    char msg[256] = {0};
+    void fail(const char *m) { std::lock_guard<std::mutex> l(mu); if (!failed) { failed = true; snprintf(msg, sizeof(msg), "%s", m); } cv.notify_all(); }
+};
+bool read_luma(FILE *f, long long frame, size_t fpx, uint8_t *dst)
+{
+    if (fseeko(f, (off_t)(frame * (long long)(fpx + fpx / 2)), SEEK_SET) != 0) return false;     // yuv_data.cpp:32-38
+    return fread(dst, 1, fpx, f) == fpx;
+}
+}  // namespace
+
+int qv_stream_yuv(qv_net *net, const char *anchor_yuv, const char *ori_yuv, const char *recon_yuv, int first_frame, int n_frames,
+                  int64_t *sse_before, int64_t *sse_after)
+{
+    if (!net || !anchor_yuv || first_frame < 0 || n_frames < 0) { set_error("qv_stream_yuv: bad argument"); return QV_ERR_ARG; }
+    if ((sse_before || sse_after) && !ori_yuv) { set_error("qv_stream_yuv: an SSE was asked for but no original file given"); return QV_ERR_ARG; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    if (sse_before) *sse_before = 0;
+    if (sse_after) *sse_after = 0;
+    if (n_frames == 0) return QV_OK;
+    const size_t fpx = (size_t)net->H * net->W;
+    const int C = net->batch, NS = 3;
+    FILE *fa = fopen(anchor_yuv, "rb"), *fo = ori_yuv ? fopen(ori_yuv, "rb") : nullptr, *fr = nullptr;
+    if (!fa) { set_error("open file failed. (%s)", anchor_yuv); return QV_ERR_IO; }                       // yuv_data.cpp:19-31
+    if (ori_yuv && !fo) { fclose(fa); set_error("open file failed. (%s)", ori_yuv); return QV_ERR_IO; }
+    if (recon_yuv) {
+        fr = fopen(recon_yuv, "r+b");                       // several ranks may fill one file, each its own frame range
+        if (!fr) fr = fopen(recon_yuv, "w+b");
+        if (!fr) { fclose(fa); if (fo) fclose(fo); set_error("open file failed. (%s)", recon_yuv); return QV_ERR_IO; }
+    }
+    StreamSlot slot[3];
+    StreamShared sh;
+    int64_t *d_sse = nullptr;
+    cudaError_t e = cudaMalloc(&d_sse, 2 * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemset(d_sse, 0, 2 * sizeof(int64_t));
+    for (int s = 0; s < NS && e == cudaSuccess; ++s) {
+        StreamSlot &S = slot[s];
+        e = cudaMallocHost(&S.h_in, C * fpx);
+        if (e == cudaSuccess) e = cudaMallocHost(&S.h_out, C * fpx);
+        if (e == cudaSuccess && fo) e = cudaMallocHost(&S.h_ori, C * fpx);
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_in, C * fpx);
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_out, C * fpx);
+        if (e == cudaSuccess && fo) e = cudaMalloc(&S.d_ori, C * fpx);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming);
+    }
+    const int nchunk = (n_frames + C - 1) / C;
+    auto cleanup = [&]() {
+        for (int s = 0; s < NS; ++s) {
+            StreamSlot &S = slot[s];
+            if (S.st) cudaStreamSynchronize(S.st);
+            cudaFreeHost(S.h_in); cudaFreeHost(S.h_out); cudaFreeHost(S.h_ori);
+            cudaFree(S.d_in); cudaFree(S.d_out); cudaFree(S.d_ori);
+            if (S.done) cudaEventDestroy(S.done);
+            if (S.st) cudaStreamDestroy(S.st);
+        }
+        cudaFree(d_sse);
+        fclose(fa); if (fo) fclose(fo); if (fr) fclose(fr);
+    };
+    if (e != cudaSuccess) { cleanup(); set_error("qv_stream_yuv: %s", cudaGetErrorString(e)); return QV_ERR_CUDA; }
+
+    // reader: files -> pinned memory, one chunk ahead of the GPU
+    std::thread reader([&] {
+        for (int k = 0; k < nchunk; ++k) {
+            StreamSlot &S = slot[k % NS];
+            {
+                std::unique_lock<std::mutex> l(sh.mu);
+                sh.cv.wait(l, [&] { return S.state == 0 || sh.failed; });
+                if (sh.failed) return;
+            }
+            const int f0 = k * C, c = std::min(C, n_frames - f0);
+            for (int j = 0; j < c; ++j) {
+                if (!read_luma(fa, (long long)first_frame + f0 + j, fpx, S.h_in + (size_t)j * fpx) ||
+                    (fo && !read_luma(fo, (long long)first_frame + f0 + j, fpx, S.h_ori + (size_t)j * fpx))) {
+                    sh.fail("qv_stream_yuv: short read (file smaller than the requested frame range)");
+                    return;
+                }
+            }
+            { std::lock_guard<std::mutex> l(sh.mu); S.f0 = f0; S.c = c; S.state = 1; }
+            sh.cv.notify_all();
+        }
+    });
+    // writer: pinned memory -> recon file, one chunk behind the GPU
+    const int dev = net->dev;
+    std::thread writer([&] {
+        cudaSetDevice(dev);
+        std::vector<uint8_t> zeros(fpx / 2, 0);
+        for (int k = 0; k < nchunk; ++k) {
+            StreamSlot &S = slot[k % NS];
+            {
+                std::unique_lock<std::mutex> l(sh.mu);
+                sh.cv.wait(l, [&] { return S.state == 2 || sh.failed; });
+                if (sh.failed) return;
+            }
+            if (cudaEventSynchronize(S.done) != cudaSuccess) { sh.fail("qv_stream_yuv: the GPU stage failed"); return; }
+            if (fr) {
+                bool ok = fseeko(fr, (off_t)(((long long)first_frame + S.f0) * (long long)(fpx + fpx / 2)), SEEK_SET) == 0;
+                for (int j = 0; j < S.c && ok; ++j)                                          // yuv_data.cpp:119-125
+                    ok = fwrite(S.h_out + (size_t)j * fpx, 1, fpx, fr) == fpx && fwrite(zeros.data(), 1, fpx / 2, fr) == fpx / 2;
+                if (!ok) { sh.fail("qv_stream_yuv: write to the reconstruction file failed"); return; }
+            }
+            { std::lock_guard<std::mutex> l(sh.mu); S.state = 0; }
+            sh.cv.notify_all();
+        }
+    });
+    // GPU stage, in chunk order
+    for (int k = 0; k < nchunk && rc == QV_OK; ++k) {
+        StreamSlot &S = slot[k % NS];
+        {
+            std::unique_lock<std::mutex> l(sh.mu);
+            sh.cv.wait(l, [&] { return S.state == 1 || sh.failed; });
+            if (sh.failed) break;
+        }
+        const size_t bytes = (size_t)S.c * fpx;
+        e = cudaMemcpyAsync(S.d_in, S.h_in, bytes, cudaMemcpyHostToDevice, S.st);
+        if (e == cudaSuccess && fo) e = cudaMemcpyAsync(S.d_ori, S.h_ori, bytes, cudaMemcpyHostToDevice, S.st);
+        if (e == cudaSuccess) {
+            rc = run_forward(net, S.d_in, S.d_out, S.c, net->H, net->W, S.st);
+            if (rc == QV_OK && fo) {
+                e = sse_accumulate(S.d_in, S.d_ori, bytes, d_sse + 0, S.st);
+                if (e == cudaSuccess) e = sse_accumulate(S.d_out, S.d_ori, bytes, d_sse + 1, S.st);
+            }
+        }
+        if (e == cudaSuccess && rc == QV_OK) e = cudaMemcpyAsync(S.h_out, S.d_out, bytes, cudaMemcpyDeviceToHost, S.st);
+        if (e == cudaSuccess && rc == QV_OK) e = cudaEventRecord(S.done, S.st);
+        if (e != cudaSuccess) { set_error("qv_stream_yuv: %s", cudaGetErrorString(e)); rc = QV_ERR_CUDA; }
+        if (rc != QV_OK) { sh.fail("qv_stream_yuv: the GPU stage failed"); break; }
+        { std::lock_guard<std::mutex> l(sh.mu); S.state = 2; }
+        sh.cv.notify_all();
+    }
+    reader.join();
+    writer.join();
+    int64_t h_sse[2] = {0, 0};
+    if (rc == QV_OK && !sh.failed) {
+        for (int s = 0; s < NS; ++s) cudaStreamSynchronize(slot[s].st);
+        if (cudaMemcpy(h_sse, d_sse, sizeof(h_sse), cudaMemcpyDeviceToHost) != cudaSuccess) rc = QV_ERR_CUDA;
+    }
+    cleanup();
+    if (rc == QV_OK && sh.failed) { set_error("%s", sh.msg); rc = strstr(sh.msg, "GPU") ? QV_ERR_CUDA : QV_ERR_IO; }
+    if (rc != QV_OK) return rc;
+    if (sse_before) *sse_before = h_sse[0];
+    if (sse_after) *sse_after = h_sse[1];
     return kernel_report(net);
 }
 
