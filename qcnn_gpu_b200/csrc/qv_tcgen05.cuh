@@ -44,15 +44,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: returns false (instead of hanging the GPU) if the phase does not complete within
-// max_cycles SM clocks (default ~2 s).
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, long long max_cycles = 4000000000LL)
+// Same with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires,
+// instead of coming back to re-issue the poll -- fewer instructions of a waiting warp in everybody else's way.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: returns false (instead of hanging the GPU) if the phase does not complete within ~0.2 s
+// (20 000 polls of up to 10 us each).
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 20000)
 {
     if (mbar_try_wait(bar, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity))
-        if (clock64() - t0 > max_cycles) return false;
-    return true;
+    for (int n = 0; n < max_polls; ++n)
+        if (mbar_try_wait_hint(bar, parity, 10000u)) return true;
+    return false;
 }
 
 // Generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma / tcgen05.cp reads).
