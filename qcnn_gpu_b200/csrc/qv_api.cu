@@ -608,6 +608,12 @@ int qv_stream_yuv(qv_net *net, const char *anchor_yuv, const char *ori_yuv, cons
         }
     });
     // GPU stage, in chunk order
+    const bool fused_path = net->impl == QV_IMPL_FUSED || (net->impl == QV_IMPL_AUTO && net->fm);
+    cudaEvent_t ev_compute = nullptr;
+    if (!fused_path && cudaEventCreateWithFlags(&ev_compute, cudaEventDisableTiming) != cudaSuccess) {
+        sh.fail("qv_stream_yuv: the GPU stage failed");
+        rc = QV_ERR_CUDA;
+    }
     for (int k = 0; k < nchunk && rc == QV_OK; ++k) {
         StreamSlot &S = slot[k % NS];
         {
@@ -618,8 +624,11 @@ int qv_stream_yuv(qv_net *net, const char *anchor_yuv, const char *ori_yuv, cons
         const size_t bytes = (size_t)S.c * fpx;
         e = cudaMemcpyAsync(S.d_in, S.h_in, bytes, cudaMemcpyHostToDevice, S.st);
         if (e == cudaSuccess && fo) e = cudaMemcpyAsync(S.d_ori, S.h_ori, bytes, cudaMemcpyHostToDevice, S.st);
+        // the layered path's launches share the handle's activation scratch: keep them in order across the slots' streams
+        if (e == cudaSuccess && !fused_path && k > 0) e = cudaStreamWaitEvent(S.st, ev_compute, 0);
         if (e == cudaSuccess) {
             rc = run_forward(net, S.d_in, S.d_out, S.c, net->H, net->W, S.st);
+            if (rc == QV_OK && !fused_path) e = cudaEventRecord(ev_compute, S.st);
             if (rc == QV_OK && fo) {
                 e = sse_accumulate(S.d_in, S.d_ori, bytes, d_sse + 0, S.st);
                 if (e == cudaSuccess) e = sse_accumulate(S.d_out, S.d_ori, bytes, d_sse + 1, S.st);
@@ -634,6 +643,7 @@ int qv_stream_yuv(qv_net *net, const char *anchor_yuv, const char *ori_yuv, cons
     }
     reader.join();
     writer.join();
+    if (ev_compute) { for (int s = 0; s < NS; ++s) cudaStreamSynchronize(slot[s].st); cudaEventDestroy(ev_compute); }
     int64_t h_sse[2] = {0, 0};
     if (rc == QV_OK && !sh.failed) {
         for (int s = 0; s < NS; ++s) cudaStreamSynchronize(slot[s].st);

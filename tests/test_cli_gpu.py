@@ -58,7 +58,8 @@ def test_cli_missing_model_exits_like_the_reference(tmp_path):
     assert p.returncode == 1 and "cannot open model file." in p.stdout        # inference/qvrcnn.cu:50-54
 
 
-def test_stream_yuv_equals_in_memory_path(tmp_path, models):
+@pytest.mark.parametrize("impl", ["fused", "layered"])
+def test_stream_yuv_equals_in_memory_path(tmp_path, models, impl):
     """qv_stream_yuv (files in, file out, reader / GPU / writer overlapped) against the in-memory path:
     same reconstruction file bytes as save_recon_as, same exact SSEs, frame ranges writable independently, and
     chunking that does not divide the frame count."""
@@ -70,6 +71,7 @@ def test_stream_yuv_equals_in_memory_path(tmp_path, models):
     _write_yuv(tmp_path / "anchor.yuv", anchor, 0x33)
     net = api.QVRCNN(0, 4, 1, h, w)                       # chunks of 4: 4 + 4 + 3
     net.load_static_para_mem(formats.write_model_vect_c(models[qp]))
+    net.set_impl(api.IMPL_FUSED if impl == "fused" else api.IMPL_LAYERED)
     want = net.forward_frames_host(anchor)
     assert np.array_equal(want[0], oracle.OracleModel(formats.write_model_vect_c(models[qp])).forward_blu(anchor[0:1])[0])
     sb, sa = net.stream_yuv(str(tmp_path / "anchor.yuv"), str(tmp_path / "ori.yuv"), str(tmp_path / "recon.yuv"), 0, frames)
