@@ -170,6 +170,12 @@ QV_API int qv_write_quant_params_cpp(const char *filename, const double *rows36)
 QV_API int qv_quantize_layer(const float *w, size_t n_w, const float *b, size_t n_b, double stepw, double ratio,
                              int8_t *w_q, int32_t *b_q);
 
+/* Host frame buffers for the vrcnn_data shim (the reference mallocs ori / input / recon, inference/yuv_data.cpp:3-14):
+   page-locked when a CUDA device is present, so that the driver's per-frame load_data and its cudaMemcpy of x_rec
+   (inference/kernel.cu:93,96) are plain DMA; plain malloc otherwise.  Free with qv_host_free. */
+QV_API void *qv_host_alloc(size_t bytes);
+QV_API void qv_host_free(void *p);
+
 /* ---- luma frame I/O + PSNR: vrcnn_data (inference/yuv_data.h:11-27) ---------------------- */
 /* vrcnn_data::read_data   inference/yuv_data.cpp:15-42: luma of the first `frames` frames of
    a YUV 4:2:0 8-bit planar file. */

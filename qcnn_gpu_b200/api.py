@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "qv_load_static_para_mem", "qv_load_static_para_hwcn", "qv_load_quant_params", "qv_read_quant_params",
     "qv_set_weights", "qv_get_quant_params", "qv_load_data", "qv_forward_blu", "qv_get_recon",
     "qv_forward_frames_host", "qv_stream_yuv", "qv_forward_frames_device", "qv_forward_rows_device", "qv_device_buffers",
-    "qv_sse_device",
+    "qv_sse_device", "qv_host_alloc", "qv_host_free",
     "qv_set_impl", "qv_get_impl", "qv_launch_count", "qv_get_activation",
     "qv_convert_model_hwcn_to_vect_c", "qv_yuv_read_luma", "qv_yuv_read_frame", "qv_yuv_write_recon",
     "qv_psnr", "qv_psnr_from_sse", "qv_solve_quant_params", "qv_write_quant_params_cpp", "qv_quantize_layer",
@@ -68,6 +68,10 @@ def lib():
         L.qv_get_recon.argtypes = [vp, vp]
         L.qv_forward_frames_host.argtypes = [vp, vp, vp, i32]
         L.qv_forward_frames_device.argtypes = [vp, vp, vp, i32, vp]
+        L.qv_host_alloc.argtypes = [C.c_size_t]
+        L.qv_host_alloc.restype = vp
+        L.qv_host_free.argtypes = [vp]
+        L.qv_host_free.restype = None
         L.qv_stream_yuv.argtypes = [vp, cp, cp, cp, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.qv_forward_rows_device.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp]
         L.qv_sse_device.argtypes = [vp, vp, C.c_size_t, vp, vp]

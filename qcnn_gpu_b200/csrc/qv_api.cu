@@ -657,6 +657,25 @@ int qv_stream_yuv(qv_net *net, const char *anchor_yuv, const char *ori_yuv, cons
     return kernel_report(net);
 }
 
+void *qv_host_alloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    void *p = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) return p;
+    cudaGetLastError();
+    return malloc(bytes);
+}
+
+void qv_host_free(void *p)
+{
+    if (!p) return;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost) { cudaFreeHost(p); return; }
+    cudaGetLastError();
+    free(p);
+}
+
 int qv_device_buffers(qv_net *net, void **d_x, void **d_x_rec)
 {
     if (!net) { set_error("qv_device_buffers: null handle"); return QV_ERR_ARG; }

@@ -16,9 +16,11 @@ public:
     vrcnn_data(int frame, int height, int width)                      // yuv_data.cpp:3-14
         : frame(frame), h(height), w(width), nSize(frame * height * width), xSize(0)
     {
-        ori = new datatype[nSize];
-        input = new datatype[nSize];
-        recon = new datatype[nSize];
+        // page-locked (qv_host_alloc): the driver's per-frame load_data / cudaMemcpy of x_rec become plain DMA
+        ori = static_cast<datatype *>(qv_host_alloc((size_t)nSize));
+        input = static_cast<datatype *>(qv_host_alloc((size_t)nSize));
+        recon = static_cast<datatype *>(qv_host_alloc((size_t)nSize));
+        if (!ori || !input || !recon) { printf("vrcnn_data: out of memory\n"); exit(1); }
     }
     int read_data(const char *orifile, const char *inputfile)          // yuv_data.cpp:15-42
     {
@@ -50,7 +52,7 @@ public:
         if (qv_yuv_write_recon(filename, recon, frame, h, w)) printf("write file failed\n");
         return 0;
     }
-    ~vrcnn_data(void) { delete[] ori; delete[] input; delete[] recon; }
+    ~vrcnn_data(void) { qv_host_free(ori); qv_host_free(input); qv_host_free(recon); }
     vrcnn_data(const vrcnn_data &) = delete;
     vrcnn_data &operator=(const vrcnn_data &) = delete;
 
