@@ -154,3 +154,18 @@ def test_no_gpu_fails_loudly():
     with pytest.raises(api.QVError) as e:
         api.QVRCNN(0, 1, 1, 16, 16)
     assert e.value.code == -3 and "no CUDA device" in str(e.value)
+
+
+def test_host_alloc_falls_back_to_malloc_without_a_gpu():
+    """qv_host_alloc / qv_host_free (the vrcnn_data shim's frame buffers): page-locked on a GPU box, plain malloc here."""
+    import ctypes
+    L = api.lib()
+    p = L.qv_host_alloc(1 << 20)
+    assert p
+    ctypes.memset(p, 0x5A, 1 << 20)
+    assert ctypes.string_at(p + (1 << 20) - 4, 4) == b"\x5a" * 4
+    L.qv_host_free(p)
+    L.qv_host_free(None)
+    q = L.qv_host_alloc(0)
+    assert q
+    L.qv_host_free(q)
