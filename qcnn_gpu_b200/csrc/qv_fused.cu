@@ -132,7 +132,7 @@ struct FusedParams {
     long long *dbg;                    // optional per-block phase timers (QV_FUSED_PROFILE=1), else null
     uint32_t sbase16, tmem_base;       // what the operand table was built for (checked by the kernel)
     int *fail_flag;                    // mapped host memory: a CTA that detects a failure reports it here
-    int dbg_flags;                     // tuning experiments only (QV_FUSED_EXPERIMENT): 1 = issue no MMAs, 2 = workers skip the drains
+    int dbg_flags;                     // profiling build only (QV_FUSED_PROFILE + QV_FUSED_EXPERIMENT): 1 = issue no MMAs, 2 = skip the drains
     int bias[BIAS_INTS];               // per accumulator column: layer bias (+ rounding bias on the FAST path)
 };
 
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         // computed up front, so that between two MMAs there is one add per operand: the tensor-pipe queue
         // is short, and a long scalar stretch in this warp drains it.
         constexpr uint64_t HI = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
-        const bool issue = leader && !(P.dbg_flags & 1);
+        const bool issue = leader && !(PROF && (P.dbg_flags & 1));        // the experiment flags only exist in the profiling build
         long long *stamp = nullptr;                                            // profile mode: clock after every MMA issue
         auto MMA = [&](auto col, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
             if (issue) mma_i8_ss_col<decltype(col)::value>(d, HI | a_lo, HI | b_lo, idesc, acc);
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
                     ++ev_work;
                 }
-                if (!(EXP & 1) && !(P.dbg_flags & 2) && i >= 3) {
+                if (!(EXP & 1) && !(PROF && (P.dbg_flags & 2)) && i >= 3) {
                     const uint8_t *row = sm + OFF_A3 + c3 * A2_ROW + (7 + mo) * 16;      // slot (R1-9) mod 3 = R1 mod 3, pixel 7 + mo + dx
                     int acc[3] = {0, 0, 0};
                     uint4 v[3];
