@@ -58,13 +58,14 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parit
         : "memory");
     return ok != 0;
 }
-// Bounded wait: returns false (instead of hanging the GPU) if the phase does not complete within ~0.2 s
-// (20 000 polls of up to 10 us each).
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 20000)
+// Bounded wait: returns false (instead of hanging the GPU) if the phase does not complete within max_polls polls
+// (each try_wait blocks for a hardware-defined time slice, ~0.2 s in total).  Measured (tools/umma_probe3.cu pingpong,
+// profiles/r1_probe3_pingpong.log): an arrive is seen 194 cycles later by a warp spinning on try_wait or test_wait, but
+// 398 cycles later by one parked with a 10 us suspend-time hint -- so: spin.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 4000000)
 {
-    if (mbar_try_wait(bar, parity)) return true;
     for (int n = 0; n < max_polls; ++n)
-        if (mbar_try_wait_hint(bar, parity, 10000u)) return true;
+        if (mbar_try_wait(bar, parity)) return true;
     return false;
 }
 

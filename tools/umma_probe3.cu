@@ -457,6 +457,106 @@ static void burst_case(long long *dC, int *dSt)
     printf("burst N=%3d k=%2d MMAs: issued after %lld cycles, complete (commit seen) after %lld  timeout=%d\n", N, K, c[0], c[1], st);
 }
 
+// ---- handshake latencies: what one leg of the MMA-warp / worker ping-pong costs ---------------------------------------
+// mode 0: pure mbarrier ping-pong between warp 0 and warp 1 (arrive -> try_wait sees it), round trip / 2
+// mode 1: warp 0 issues one small MMA (N = 16) + tcgen05.commit, warp 1 waits for the commit and arrives back
+// mode 2: as mode 1 with `k` wide MMAs (N = 128) queued before the commit (latency from LAST issue to commit seen = total - issue)
+template <int W>
+__device__ __forceinline__ bool pp_wait(uint64_t *bar, uint32_t parity)
+{
+    if (W == 0) return mbar_wait(bar, parity);                       // the product's wait: try_wait + suspend-time hint
+    if (W == 1) {                                                    // try_wait without a hint, spinning
+        for (int n = 0; n < 4000000; ++n) if (mbar_try_wait(bar, parity)) return true;
+        return false;
+    }
+    for (int n = 0; n < 40000000; ++n) {                             // test_wait: non-blocking poll
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+        if (W == 3) __nanosleep(20);
+    }
+    return false;
+}
+template <int W>
+__global__ void k_pingpong(int mode, int kmma, int rounds, long long *cycles, int *status)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint64_t bar_a[2], bar_b[2];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (32768 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sm)[i] = 0x01010101u;
+    fence_proxy_async_smem();
+    if (tid == 0) { for (int i = 0; i < 2; ++i) { mbar_init(&bar_a[i], 1); mbar_init(&bar_b[i], 1); } mbar_fence_init(); }
+    if (warp == 0) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = s_tmem;
+    bool ok = true;
+    if (warp == 0) {
+        const uint64_t ad = smem_desc(smem_u32(sm), 16384, 128), bd = smem_desc(smem_u32(sm) + 32768, 128 * 16, 128);
+        long long t_issue = 0;
+        const long long t0 = clock64();
+        for (int r = 0; r < rounds; ++r) {
+            if (lane == 0) {
+                if (mode == 0) mbar_arrive(&bar_a[r & 1]);
+                else {
+                    const long long ti = clock64();
+                    for (int j = 0; j < kmma; ++j) mma_col<0>(tm, ad, bd, idesc_i8(128, mode == 1 ? 16 : 128), 1);
+                    mma_commit(&bar_a[r & 1]);
+                    t_issue += clock64() - ti;
+                }
+                ok &= pp_wait<W>(&bar_b[r & 1], (r >> 1) & 1);
+            }
+            __syncwarp();
+            fence_after_sync();
+        }
+        if (lane == 0) { cycles[0] = clock64() - t0; cycles[1] = t_issue; status[0] = ok ? 0 : 1; }
+    } else if (warp == 1) {
+        for (int r = 0; r < rounds; ++r) {
+            if (lane == 0) ok &= pp_wait<W>(&bar_a[r & 1], (r >> 1) & 1);
+            __syncwarp();
+            fence_after_sync();
+            fence_before_sync();
+            if (lane == 0) mbar_arrive(&bar_b[r & 1]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// ---- the same ping-pong through plain shared-memory counters (red.shared + ld.volatile.shared spin) instead of mbarriers ----
+__global__ void k_pingpong_flag(int rounds, int nwait_warps, long long *cycles)
+{
+    __shared__ unsigned int ca, cb;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { ca = 0; cb = 0; }
+    __syncthreads();
+    volatile unsigned int *va = &ca, *vb = &cb;
+    if (warp == 0) {
+        const long long t0 = clock64();
+        for (int r = 1; r <= rounds; ++r) {
+            if (lane == 0) {
+                atomicAdd(&ca, 1u);
+                while (*vb < (unsigned)(r * nwait_warps)) { }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) cycles[0] = clock64() - t0;
+    } else if (warp <= nwait_warps) {
+        for (int r = 1; r <= rounds; ++r) {
+            if (lane == 0) {
+                while (*va < (unsigned)r) { }
+                __threadfence_block();
+                atomicAdd(&cb, 1u);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 int main(int argc, char **argv)
 {
     cudaDeviceProp p;
@@ -495,6 +595,37 @@ int main(int argc, char **argv)
         CK(cudaMalloc(&dC, 64)); CK(cudaMalloc(&dSt, 4));
         cont_case<4>(dC, dSt, 2, 0); cont_case<6>(dC, dSt, 2, 0); cont_case<7>(dC, dSt, 2, 0); cont_case<8>(dC, dSt, 2, 0); cont_case<9>(dC, dSt, 2, 0);
         cont_case<9>(dC, dSt, 1, 0); cont_case<9>(dC, dSt, 4, 0); cont_case<9>(dC, dSt, 2, 1);
+    }
+    if (!strcmp(t, "pingpong") || !strcmp(t, "all")) {
+        long long *dC; int *dSt;
+        CK(cudaMalloc(&dC, 64)); CK(cudaMalloc(&dSt, 4));
+        const int rounds = 2000;
+        const int cfg[][2] = {{0, 0}, {1, 1}, {2, 1}, {2, 8}};
+        auto run = [&](auto kern, const char *wname) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8192));
+            for (auto &c : cfg) {
+                long long h[2]; int st = 0;
+                for (int rep = 0; rep < 2; ++rep) {
+                    CK(cudaMemset(dSt, 0, 4));
+                    kern<<<1, 64, 32768 + 8192>>>(c[0], c[1], rounds, dC, dSt);
+                    CK(cudaDeviceSynchronize());
+                }
+                CK(cudaMemcpy(h, dC, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost));
+                if (c[0] == 0) printf("pingpong [%s] mbarrier only: %.0f cycles per round trip (two legs)  timeout=%d\n", wname, (double)h[0] / rounds, st);
+                else printf("pingpong [%s] %d x MMA N=%d + commit -> seen -> arrive -> seen: %.0f cycles per round, of which issuing %.0f  timeout=%d\n",
+                            wname, c[1], c[0] == 1 ? 16 : 128, (double)h[0] / rounds, (double)h[1] / rounds, st);
+            }
+        };
+        run(k_pingpong<0>, "try_wait + 10 us hint");
+        run(k_pingpong<1>, "try_wait, no hint");
+        run(k_pingpong<2>, "test_wait spin");
+        run(k_pingpong<3>, "test_wait + nanosleep(20)");
+        for (int nw : {1, 8, 12}) {
+            long long h[1];
+            for (int rep = 0; rep < 2; ++rep) { k_pingpong_flag<<<1, 32 * (nw + 1)>>>(rounds, nw, dC); CK(cudaDeviceSynchronize()); }
+            CK(cudaMemcpy(h, dC, 8, cudaMemcpyDeviceToHost));
+            printf("pingpong [smem counters, atomicAdd + volatile spin] 1 signaller, %d waiting warps that all answer: %.0f cycles per round trip\n", nw, (double)h[0] / rounds);
+        }
     }
     return 0;
 }
