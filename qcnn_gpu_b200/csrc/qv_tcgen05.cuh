@@ -58,16 +58,29 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parit
         : "memory");
     return ok != 0;
 }
-// Bounded wait: returns false (instead of hanging the GPU) if the phase does not complete within max_polls polls
-// (each try_wait blocks for a hardware-defined time slice, ~0.2 s in total).  Measured (tools/umma_probe3.cu pingpong,
-// profiles/r1_probe3_pingpong.log): an arrive is seen 194 cycles later by a warp spinning on try_wait or test_wait, but
-// 398 cycles later by one parked with a 10 us suspend-time hint -- so: spin.
+// Bounded wait: returns false (instead of hanging the GPU) if the phase does not complete within ~0.2 s (20 000 polls of
+// up to 10 us each).  The waiter parks in hardware with a suspend-time hint.  A parked waiter sees an arrive later than one
+// that spins on try_wait (398 against 194 cycles, tools/umma_probe3.cu pingpong, profiles/r1_probe3_pingpong.log), and yet
+// the fused kernel is 10 % FASTER with parked waiters (6.60 against 7.25 ms, same box, same call:
+// profiles/experiments/r1_wait_spin_vs_hint_and_three_workers_ab.log).  It is the MMA warp's own spinning that costs: with
+// only that warp spinning 6.97 ms, with only the workers spinning 6.62 ms (r1_split_commit_v2_and_hybrid_wait_ab.log).
+// QV_WAIT_SPIN builds the spinning form.
+#ifdef QV_WAIT_SPIN
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 4000000)
 {
     for (int n = 0; n < max_polls; ++n)
         if (mbar_try_wait(bar, parity)) return true;
     return false;
 }
+#else
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 20000)
+{
+    if (mbar_try_wait(bar, parity)) return true;
+    for (int n = 0; n < max_polls; ++n)
+        if (mbar_try_wait_hint(bar, parity, 10000u)) return true;
+    return false;
+}
+#endif
 
 // Generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma / tcgen05.cp reads).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
