@@ -47,8 +47,9 @@
 //                operand of a1 row R1+1 (im2col, three stages), C4 on a3 row R1-9 (9 LDS.128 + 108 dp4a per
 //                pixel, two running sums carry the partial output rows), applyRes_y and the store of output row
 //                R1-10.
-// Workers and C4 warps arrive on one mbarrier pair that releases the next MMAs, the MMA warp commits to another
-// pair that releases the workers, and a named barrier per iteration publishes the a3 rows to the C4 warps.
+// Workers and C4 warps arrive on a named barrier (three ids in rotation) in which the MMA warp blocks before it issues the
+// next MMAs, the MMA warp commits to an mbarrier pair that releases the workers, and a second named barrier per iteration
+// publishes the a3 rows to the C4 warps.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -167,6 +168,17 @@ __device__ __forceinline__ void warp_wait(uint64_t *bar, uint32_t parity, int la
     __syncwarp();
 }
 
+// workers / C4 warps -> MMA warp, event ev: every lane arrives on named barrier 2 + ev mod 3, the MMA warp blocks in
+// bar.sync on the same id.  A warp blocked there issues nothing (a warp polling an mbarrier does, and on the MMA warp's SM
+// sub-partition that is measurable: DESIGN.md section 7) and is released ~40 cycles after the last arrival.  Three ids are
+// enough: a C4 warp arrives for event k after the named barrier that ended iteration k-2, which the workers reach only after
+// the commit of iteration k-3, which the MMA warp issues after it has passed event k-3; the workers arrive later still.  So
+// the arrivals for event k cannot begin before the MMA warp has left the barrier of event k-3, the previous user of that id.
+__device__ __forceinline__ void work_arrive(uint32_t ev)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(2u + ev % 3u), "n"(NWORKER + NC4 + 32) : "memory");
+}
+
 // ---- requantise 16 accumulator columns of this thread's pixel and store them as one 16-byte
 // ---- channel group of an activation row (mat.cu:262-303 folded into the TMEM epilogue)
 template <bool FAST, int BOFF>
@@ -225,11 +237,10 @@ template <bool FAST, bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ FusedParams P)
 {
     extern __shared__ __align__(1024) uint8_t sm[];
-    // Two mbarriers per direction, used alternately (event e -> barrier e&1, parity (e>>1)&1): a
-    // waiter can then never be lapped, because the second-next completion of the SAME barrier
-    // needs the waiter's own arrival in between.
-    uint64_t *bar_work = reinterpret_cast<uint64_t *>(sm + OFF_CTRL);        // [2] workers -> MMA
-    uint64_t *bar_mma = bar_work + 2;                                        // [2] MMA (tcgen05.commit) -> workers
+    // MMA warp (tcgen05.commit) -> workers: two mbarriers used alternately (event e -> barrier e&1, parity (e>>1)&1).  A
+    // waiter can then never be lapped: the second-next completion of the SAME barrier needs the waiter's own arrival
+    // (work_arrive) in between.  The other direction is a named barrier, see work_arrive.
+    uint64_t *bar_mma = reinterpret_cast<uint64_t *>(sm + OFF_CTRL);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(sm + OFF_CTRL + 32);
     int *s_fail = reinterpret_cast<int *>(sm + OFF_CTRL + 36);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -241,8 +252,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     for (int i = tid; i < (OFF_CTRL - OFF_A1) / 16; i += NTHREADS)      // finite data everywhere the MMAs may read
         reinterpret_cast<uint4 *>(sm + OFF_A1)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        mbar_init(&bar_work[0], (NWORKER + NC4) / 32);          // every worker warp and every C4 warp arrives
-        mbar_init(&bar_work[1], (NWORKER + NC4) / 32);
         mbar_init(&bar_mma[0], 1);
         mbar_init(&bar_mma[1], 1);
         *s_fail = 0;
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         // The whole warp runs the control flow (so that descriptors stay in uniform registers);
         // one elected lane issues the tcgen05 instructions.
         const bool leader = elect_one();
-        uint32_t ev_work = 0, ev_mma = 0;
+        uint32_t nb3 = 0, ev_mma = 0;
         long long t_wait = 0, t_issue = 0, tc0 = PROF ? clock64() : 0;
         // Descriptors are handled as their low 32-bit word in 16-byte units: (smem address >> 4) | (LBO >> 4) << 16;
         // the high word (SBO = 128 B, version 1) is a constant.  Everything that changes per iteration is
@@ -290,8 +299,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             PhaseBases pb_next = c_phase[ph];
             for (int i = 0; i < niter; ++i) {
                 const PhaseBases pb = pb_next;                    // this iteration's operand bases (loaded one iteration ago)
-                warp_wait(&bar_work[ev_work & 1], (ev_work >> 1) & 1, lane, s_fail);
-                ++ev_work;
+                asm volatile("bar.sync %0, %1;" ::"r"(2u + nb3), "n"(NWORKER + NC4 + 32) : "memory");      // event ev_work, id 2 + ev_work mod 3
+                nb3 = nb3 == 2 ? 0 : nb3 + 1;
                 fence_after_sync();
                 bool tr = false;
                 if (PROF) {
@@ -366,8 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             const int niter = y1 - y0 + PIPE;
             // ---- prologue: the previous unit's accumulators are drained (nothing of this unit is in flight yet) ------------
             worker_bar();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+            work_arrive(ev_work);
             ++ev_work;
             int c3 = mod_pos(y0 - 4, 3), c6 = mod_pos(y0 - 4, 6);
             // image columns of this thread's a1 / a2 / a3 pixel inside the frame?  (each layer zero-pads its own input)
@@ -429,8 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 if (i + 1 < niter) {
                     fence_proxy_async_smem();
                     fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+                    work_arrive(ev_work);
                     ++ev_work;
                 }
                 lap(2);
@@ -509,8 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             worker_bar();
             im2col(y0 - 4, c3);
             fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+            work_arrive(ev_work);
             ++ev_work;
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
@@ -520,8 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 if (i + 1 < niter) {
                     if (!(EXP & 4)) im2col(R1 + 1, wrap_inc(c3, 3));
                     fence_proxy_async_smem();                     // st.shared above -> visible to the tensor core
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_work[ev_work & 1]);
+                    work_arrive(ev_work);
                     ++ev_work;
                 }
                 if (!(EXP & 1) && !(PROF && (P.dbg_flags & 2)) && i >= 3) {
