@@ -137,11 +137,12 @@ struct FusedParams {
     int bias[BIAS_INTS];               // per accumulator column: layer bias (+ rounding bias on the FAST path)
 };
 
-// Operand addresses of the 27 MMAs of one row iteration, for each of the 12 phases R1 mod 12 (the ring rotations have
-// periods 2, 3, 4 and 6).  Lives in constant memory so that the MMA warp forms its descriptors with uniform-datapath
-// loads only: measured (profiles/r1_probe3_contention*.log), integer ALU work of the worker warps that share the MMA
-// warp's SM sub-partition starves exactly the ALU-pipe instructions (address arithmetic, R2UR) an issue loop would
-// otherwise need, and the tensor pipe's queue is only a handful of instructions deep.
+// Operands of the 27 MMAs of one row iteration, for each of the 12 phases R1 mod 12 (the ring rotations have periods 2,
+// 3, 4 and 6).  PhaseBases / FixedBases are the host-side description (what rotates, what does not); PhaseOps is its
+// expansion into ready-made descriptors in constant memory, so that the MMA warp needs uniform-datapath loads only:
+// measured (profiles/r1_probe3_contention*.log), integer ALU work of the worker warps that share the MMA warp's SM
+// sub-partition starves exactly the ALU-pipe instructions (address arithmetic, R2UR) an issue loop would otherwise
+// need, and the tensor pipe's queue is only a handful of instructions deep.
 struct PhaseBases {                    // low descriptor words (16-byte units | LBO << 16) and TMEM addresses that rotate with R1
     uint32_t im, a1_r2, a2_r6, b22;    // C1 operand stage ; a1 row R1-2 ; a2 row R1-6 ; C2_2 ring window start
     uint32_t b21, b31, d1, d32;        // C2_1 / C3_1 ring window starts ; C1 / C3_2 accumulator stages
@@ -149,8 +150,12 @@ struct PhaseBases {                    // low descriptor words (16-byte units | 
 };
 struct FixedBases { uint32_t zeroA, w1, w32, r22, r21, r31, pad0, pad1; };   // what does not rotate
 constexpr int N_PHASE = 12;
-__constant__ PhaseBases c_phase[N_PHASE];
-__constant__ FixedBases c_fixed;
+constexpr int N_MMA = 27;
+struct PhaseOps {
+    uint4 ab[N_MMA];                   // {A lo, A hi, B lo, B hi} in issue order
+    uint32_t d1, d32, z22, z21, z31, pad[3];
+};
+__constant__ PhaseOps c_ops[N_PHASE];
 
 __host__ __device__ __forceinline__ int mod_pos(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
@@ -272,34 +277,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         const bool leader = elect_one();
         uint32_t nb3 = 0, ev_mma = 0;
         long long t_wait = 0, t_issue = 0, tc0 = PROF ? clock64() : 0;
-        // Descriptors are handled as their low 32-bit word in 16-byte units: (smem address >> 4) | (LBO >> 4) << 16;
-        // the high word (SBO = 128 B, version 1) is a constant.  Everything that changes per iteration is
-        // computed up front, so that between two MMAs there is one add per operand: the tensor-pipe queue
-        // is short, and a long scalar stretch in this warp drains it.
-        constexpr uint64_t HI = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
         const bool issue = leader && !(PROF && (P.dbg_flags & 1));        // the experiment flags only exist in the profiling build
         long long *stamp = nullptr;                                            // profile mode: clock after every MMA issue
-        auto MMA = [&](auto col, uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-            if (issue) mma_i8_ss_col<decltype(col)::value>(d, HI | a_lo, HI | b_lo, idesc, acc);
-            if (PROF && stamp) *stamp++ = clock64();
-        };
         constexpr std::integral_constant<int, COL_DISCARD> ONCE{};             // A tile used by this MMA only
         constexpr std::integral_constant<int, COL_FILL> KEEP{};                // A tile stays in the collector ...
         constexpr std::integral_constant<int, COL_USE> AGAIN{};                // ... is used from there and kept ...
         constexpr std::integral_constant<int, COL_LASTUSE> LAST{};             // ... and used from there for the last time
-        if ((sbase >> 4) != P.sbase16 || tm != P.tmem_base) { if (lane == 0) *s_fail = 2; }     // c_phase / c_fixed do not describe this CTA
-        constexpr uint32_t LP = (uint32_t)(PLANE >> 4) << 16;                  // LBO = one plane: K-halves are planes p, p+1
-        constexpr uint32_t LX = 1u << 16;                                      // LBO = 16 B: K-halves are pixels x, x+1 of one plane
-        const FixedBases fb = c_fixed;
+        if ((sbase >> 4) != P.sbase16 || tm != P.tmem_base) { if (lane == 0) *s_fail = 2; }     // c_ops does not describe this CTA
+        const uint32_t r22 = tm + TM_R22, r21 = tm + TM_R21, r31 = tm + TM_R31;
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg;
             const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             int ph = mod_pos(y0 - 4, N_PHASE);
-            PhaseBases pb_next = c_phase[ph];
             for (int i = 0; i < niter; ++i) {
-                const PhaseBases pb = pb_next;                    // this iteration's operand bases (loaded one iteration ago)
-                asm volatile("bar.sync %0, %1;" ::"r"(2u + nb3), "n"(NWORKER + NC4 + 32) : "memory");      // event ev_work, id 2 + ev_work mod 3
+                // This iteration's operands: both descriptors of every MMA come ready-made from the phase table, one
+                // 16-byte uniform constant load per MMA.  The issue loop is what bounds the kernel, and anything else in
+                // it -- descriptor adds, high-word moves, R2UR -- showed up in the step time.
+                const PhaseOps &op = c_ops[ph];
+                auto MMA = [&](auto col, uint32_t d, int k, uint32_t idesc, uint32_t acc) {
+                    const uint4 ab = op.ab[k];
+                    if (issue) mma_i8_ss_col<decltype(col)::value>(d, ((uint64_t)ab.y << 32) | ab.x, ((uint64_t)ab.w << 32) | ab.z, idesc, acc);
+                    if (PROF && stamp) *stamp++ = clock64();
+                };
+                asm volatile("bar.sync %0, %1;" ::"r"(2u + nb3), "n"(NWORKER + NC4 + 32) : "memory");      // workers / C4 warps -> here, see work_arrive
                 nb3 = nb3 == 2 ? 0 : nb3 + 1;
                 fence_after_sync();
                 bool tr = false;
@@ -310,39 +311,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     stamp = tr ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
                 }
                 // ---- C1: a1 row R1 = im2col stage (R1 mod 3) x W1 (N = 64) -------------------------------
-                MMA(ONCE, pb.d1, pb.im, fb.w1, idesc_i8(128, 64), 0);
+                MMA(ONCE, op.d1, 0, idesc_i8(128, 64), 0);
                 // ---- the ring slots of the rows that start in this iteration: 0 = zero tile x anything ------
-                MMA(KEEP, pb.z22, fb.zeroA, fb.w1, idesc_i8(128, 16), 0);        // C2_2 row R1
-                MMA(AGAIN, pb.z21, fb.zeroA, fb.w1, idesc_i8(128, 32), 0);       // C2_1 row R1-1
-                MMA(LAST, pb.z31, fb.zeroA, fb.w1, idesc_i8(128, 16), 0);        // C3_1 row R1-5
+                MMA(KEEP, op.z22, 1, idesc_i8(128, 16), 0);         // C2_2 row R1
+                MMA(AGAIN, op.z21, 2, idesc_i8(128, 32), 0);        // C2_1 row R1-1
+                MMA(LAST, op.z31, 3, idesc_i8(128, 16), 0);         // C3_1 row R1-5
                 // ---- layer 3 on a2 row R1-6.  C3_1 (3x3, 48 -> 16) scatters into its 4-slot ring, N = 64; its K-steps
                 //      pair 16-channel units: (s: planes 0,1) x3, (s0 plane 2 | s1 plane 2), (s2 plane 2 | zero weights).
                 //      C3_2 (1x1, 48 -> 32, N = 32) needs exactly the tiles of K-steps 1 and 3 (centre pixel: planes 0,1
                 //      and zero weights | plane 2) and takes them from the collector -------------------------------------
-                MMA(ONCE, fb.r31, pb.a2_r6 + 6 + LP, pb.b31, idesc_i8(128, 64), 1);
-                MMA(KEEP, fb.r31, pb.a2_r6 + 7 + LP, pb.b31 + (T31 >> 4), idesc_i8(128, 64), 1);
-                MMA(LAST, pb.d32, pb.a2_r6 + 7 + LP, fb.w32, idesc_i8(128, 32), 0);
-                MMA(ONCE, fb.r31, pb.a2_r6 + 8 + LP, pb.b31 + 2 * (T31 >> 4), idesc_i8(128, 64), 1);
-                MMA(KEEP, fb.r31, pb.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, pb.b31 + 3 * (T31 >> 4), idesc_i8(128, 64), 1);
-                MMA(LAST, pb.d32, pb.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, fb.w32 + (T32 >> 4), idesc_i8(128, 32), 1);
-                MMA(ONCE, fb.r31, pb.a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, pb.b31 + 4 * (T31 >> 4), idesc_i8(128, 64), 1);
+                MMA(ONCE, r31, 4, idesc_i8(128, 64), 1);
+                MMA(KEEP, r31, 5, idesc_i8(128, 64), 1);
+                MMA(LAST, op.d32, 6, idesc_i8(128, 32), 0);
+                MMA(ONCE, r31, 7, idesc_i8(128, 64), 1);
+                MMA(KEEP, r31, 8, idesc_i8(128, 64), 1);
+                MMA(LAST, op.d32, 9, idesc_i8(128, 32), 1);
+                MMA(ONCE, r31, 10, idesc_i8(128, 64), 1);
                 // ---- layer 2: scatter a1 row R1-2.  C2_2 (5x5, 64 -> 16) into its 6-slot ring with N = 96, shifts
                 //      s = 0..4 (pixel 4+s) x K-halves h (planes 2h, 2h+1); C2_1 (3x3, 64 -> 32) into its 4-slot
                 //      ring with N = 128 reads the same tile for s = 1..3 and takes it from the collector.  Issued last: these
                 //      MMAs execute slower than they issue, so the tensor pipe has a backlog to work on during the handshake ---
+                int k = 11;
 #pragma unroll
                 for (int t = 0; t < 10; ++t) {
-                    const int s = t / 2, h = t & 1;
-                    const uint32_t a = pb.a1_r2 + ((h * 2 * PLANE + (4 + s) * 16) >> 4);
+                    const int s = t / 2;
                     if (s >= 1 && s <= 3) {
-                        MMA(KEEP, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
-                        MMA(LAST, fb.r21, a, pb.b21 + ((s - 1) * 2 + h) * (T21 >> 4), idesc_i8(128, 128), 1);
+                        MMA(KEEP, r22, k++, idesc_i8(128, 96), 1);
+                        MMA(LAST, r21, k++, idesc_i8(128, 128), 1);
                     } else {
-                        MMA(ONCE, fb.r22, a, pb.b22 + t * (T22 >> 4), idesc_i8(128, 96), 1);
+                        MMA(ONCE, r22, k++, idesc_i8(128, 96), 1);
                     }
                 }
                 ph = wrap_inc(ph, N_PHASE);
-                pb_next = c_phase[ph];                            // three 16-byte constant loads, in flight during the handshake
                 if (leader) mma_commit(&bar_mma[ev_mma & 1]);
                 ++ev_mma;
                 __syncwarp();
@@ -615,6 +615,36 @@ void build_mma_bases(uint32_t sb, uint32_t tm, PhaseBases *pb, FixedBases &fb)
     }
 }
 
+// The per-MMA expansion of the two tables above, in the kernel's issue order.
+void build_mma_ops(const PhaseBases *pb, const FixedBases &fb, PhaseOps *ops)
+{
+    constexpr uint32_t HI = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+    constexpr uint32_t LP = (uint32_t)(PLANE >> 4) << 16, LX = 1u << 16;
+    for (int ph = 0; ph < N_PHASE; ++ph) {
+        const PhaseBases &e = pb[ph];
+        PhaseOps &o = ops[ph];
+        o = PhaseOps{};
+        int k = 0;
+        auto put = [&](uint32_t a, uint32_t b) { o.ab[k++] = make_uint4(a, HI, b, HI); };
+        put(e.im, fb.w1);
+        put(fb.zeroA, fb.w1); put(fb.zeroA, fb.w1); put(fb.zeroA, fb.w1);
+        put(e.a2_r6 + 6 + LP, e.b31);
+        put(e.a2_r6 + 7 + LP, e.b31 + (T31 >> 4));
+        put(e.a2_r6 + 7 + LP, fb.w32);
+        put(e.a2_r6 + 8 + LP, e.b31 + 2 * (T31 >> 4));
+        put(e.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, e.b31 + 3 * (T31 >> 4));
+        put(e.a2_r6 + ((2 * PLANE) >> 4) + 6 + LX, fb.w32 + (T32 >> 4));
+        put(e.a2_r6 + ((2 * PLANE) >> 4) + 8 + LX, e.b31 + 4 * (T31 >> 4));
+        for (int t = 0; t < 10; ++t) {
+            const int sft = t / 2, h = t & 1;
+            const uint32_t a = e.a1_r2 + ((h * 2 * PLANE + (4 + sft) * 16) >> 4);
+            put(a, e.b22 + t * (T22 >> 4));
+            if (sft >= 1 && sft <= 3) put(a, e.b21 + ((sft - 1) * 2 + h) * (T21 >> 4));
+        }
+        o.d1 = e.d1; o.d32 = e.d32; o.z22 = e.z22; o.z21 = e.z21; o.z31 = e.z31;
+    }
+}
+
 }  // namespace
 
 // =================================== host side ==========================================
@@ -756,8 +786,9 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
             FixedBases fb;
             build_mma_bases(h_b[0] >> 4, h_b[1], pb, fb);
             P.sbase16 = h_b[0] >> 4; P.tmem_base = h_b[1];
-            e = cudaMemcpyToSymbolAsync(c_phase, pb, sizeof(pb), 0, cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_fixed, &fb, sizeof(fb), 0, cudaMemcpyHostToDevice, st);
+            static PhaseOps ops[N_PHASE];       // static: the async copy reads it until the synchronize below
+            build_mma_ops(pb, fb, ops);
+            e = cudaMemcpyToSymbolAsync(c_ops, ops, sizeof(ops), 0, cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         }
     }
