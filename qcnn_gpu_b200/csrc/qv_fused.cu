@@ -35,10 +35,11 @@
 //   warp 8, MMA issue : 27 MMAs per iteration -- C1 for a1 row R1 (im2col operand); the three ring-slot
 //                initialisations; C3_1 scatter and C3_2 of a2 row R1-6; C2_2 and C2_1 scatter of a1 row R1-2
 //                (the wide MMAs last: they execute slower than they issue, so the tensor pipe still has a
-//                backlog during the handshake).  Operand addresses come from a 12-phase table in constant
-//                memory (the ring rotations have periods 2, 3, 4, 6), prefetched one iteration ahead, plus
-//                uniform-datapath adds: the issue loop executes no ALU-pipe instruction, which matters because
-//                the worker warps of the same SM sub-partition saturate that pipe (profiles/r1_probe3_contention*).
+//                backlog during the handshake).  Both descriptors of every MMA come ready-made from a 12-phase table
+//                in constant memory (the ring rotations have periods 2, 3, 4, 6), one uniform load per MMA: the issue
+//                loop executes no ALU-pipe instruction, which matters because the worker warps of the same SM
+//                sub-partition saturate that pipe (profiles/r1_probe3_contention*), and it is this warp's serial
+//                work that bounds the kernel.
 //   warps 0-7, workers: drain what iteration i-1 completed, TMEM -> requantise -> st.shared: a1 row R1-1; a2 row
 //                R1-5 plane 2 (C2_2) and a2 row R1-4 planes 0,1 (C2_1); a3 row R1-8 plane 0 (C3_1) and a3 row
 //                R1-7 planes 1,2 (C3_2).  A warp can only read its own TMEM lane quarter, so two warps share a
@@ -71,7 +72,7 @@
 namespace qv {
 namespace {
 using namespace tc;
-constexpr int EXP = QV_EXP;   // timing experiments only (tools/build_variants.sh): 1 no C4 on the workers, 2 no requantiser arithmetic, 4 no im2col
+constexpr int EXP = QV_EXP;   // timing experiments only (tools/build_variants.sh): 1 no a3 requantisation and no C4, 2 no requantiser arithmetic, 4 no im2col
 
 constexpr int WT = 120;                    // output columns per strip
 constexpr int PW = 136;                    // pixel pitch of every activation row buffer
