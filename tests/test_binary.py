@@ -1,0 +1,62 @@
+"""What the shipped library contains, read from its SASS (no GPU needed): the product kernel is sm_100a code that
+issues tcgen05 MMAs (UTCIMMA) with collector reuse, drains TMEM (LDTM), commits to mbarriers (UTCBAR), waits parked
+(not spinning), and spills no registers.  Mnemonics: /opt/skills/guides/B200_PROFILING.md."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from qcnn_gpu_b200 import api
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP), reason="cuobjdump not available")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    api.lib()
+    out = subprocess.run([CUOBJDUMP, "-sass", api.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    kernels = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            kernels[name] = []
+        elif name and "/*" in line:
+            kernels[name].append(line)
+    return out, kernels
+
+
+def test_library_is_sm_100a_only(sass):
+    out, _ = sass
+    archs = set(re.findall(r"arch = (sm_\w+)", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_fused_kernel_uses_tcgen05_and_parks_its_waiters(sass):
+    _, kernels = sass
+    fused = {k: v for k, v in kernels.items() if "k_fused" in k}
+    assert len(fused) == 3, list(fused)                      # FAST, generic requantiser, FAST + profiling
+    for name, lines in fused.items():
+        text = "\n".join(lines)
+        assert len(re.findall(r"\bUTCIMMA\b", text)) == 27, name        # the 27 MMAs of one row iteration, unrolled once
+        assert "A_KEEP" in text and "A_REUSE" in text, name             # collector reuse survived the compiler
+        assert "LDTM" in text and "UTCBAR" in text, name
+        assert "NANOSLEEP" in text, name                                # mbarrier waits with a suspend-time hint
+        assert "BAR.ARV" in text, name                                  # workers -> MMA warp through a named barrier
+        if "ILb1ELb1E" not in name:                                     # (the profiling build keeps its counters in an array)
+            # no register spills: nothing is ever loaded back from local memory; the only store is printf's argument
+            assert not re.search(r"\bLDL\b", text) and len(re.findall(r"\bSTL\b", text)) <= 1, name
+    # the issue loop of the product kernel forms no descriptor with vector-ALU work: between the first and the last
+    # MMA there are only uniform-datapath instructions
+    prod = next(v for k, v in fused.items() if "ILb1ELb0E" in k)
+    ops = [l for l in (re.sub(r"^\s*/\*[0-9a-f]+\*/\s*", "", x).strip() for x in prod) if l and not l.startswith("/*")]
+    first = next(i for i, l in enumerate(ops) if "UTCIMMA" in l)
+    last = max(i for i, l in enumerate(ops) if "UTCIMMA" in l)
+    body = [l.split()[0] if not l.startswith("@") else l.split()[1] for l in ops[first:last + 1]]
+    allowed = {"UTCIMMA", "LDCU", "LDCU.64", "LDCU.128", "UMOV", "R2UR", "UIADD3", "UIMAD", "NOP", "R2UR.FILL", "MOV.SPILL"}
+    assert set(body) <= allowed, set(body) - allowed
+    assert len(body) <= 130, len(body)                                  # 27 MMAs + their table loads, little else
