@@ -1,6 +1,6 @@
 // umma_probe2 -- does tcgen05.mma.cta_group::2 (CTA pair, M = 2 x 128) work with the fused kernel's
 // operand layouts, what does an instruction cost, and can cta_group::1 MMAs be mixed in on the same TMEM?
-// Not part of the product.   usage: umma_probe2 [num|thr]
+// Not part of the product.   usage: umma_probe2 [num|thr|thrb]   (thrb: throughput with a different B tile for every MMA)
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +19,7 @@ constexpr int PX = 192, PLANE_B = PX * 16;          // A: [2 planes][192 px][16 
 constexpr int A_BYTES = 2 * PLANE_B;
 constexpr int NMAX = 256;
 constexpr int B_BYTES = 2 * NMAX * 16;              // per CTA: [2 K-chunks][N/2 rows][16 B]
+constexpr int NBT = 8;                              // thrb: B tiles to rotate through
 
 __device__ __forceinline__ uint32_t cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync()
@@ -65,10 +66,11 @@ __global__ void __cluster_dims__(2, 1, 1) k2(const int8_t *gA, const int8_t *gB,
         const int plane = i / PX, px = i % PX;
         reinterpret_cast<int4 *>(sA)[i] = reinterpret_cast<const int4 *>(gA)[(rank * 2 + plane) * PX + px];
     }
-    for (int i = tid; i < N; i += blockDim.x) {          // i = kc * (N/2) + n
-        const int kc = i / (N / 2), n = i % (N / 2);
-        reinterpret_cast<int4 *>(sB)[kc * (N / 2) + n] = reinterpret_cast<const int4 *>(gB)[(rank * (N / 2) + n) * 2 + kc];
-    }
+    for (int t = 0; t < (mode == 2 ? NBT : 1); ++t)
+        for (int i = tid; i < N; i += blockDim.x) {      // i = kc * (N/2) + n
+            const int kc = i / (N / 2), n = i % (N / 2);
+            reinterpret_cast<int4 *>(sB + t * N * 16)[kc * (N / 2) + n] = reinterpret_cast<const int4 *>(gB)[(rank * (N / 2) + n) * 2 + kc];
+        }
     fence_proxy_async_smem();
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc2(&s_tmem, 256);
@@ -90,7 +92,7 @@ __global__ void __cluster_dims__(2, 1, 1) k2(const int8_t *gA, const int8_t *gB,
             for (int o = 0; o < 64; ++o)
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (leader) mma2_i8_ss(tm, ad + (uint64_t)((j * 5) % 60), bd, id, (o | j) != 0);
+                    if (leader) mma2_i8_ss(tm, ad + (uint64_t)((j * 5) % 60), bd + (uint64_t)(mode == 2 ? ((j * 3) % NBT) * N : 0), id, (o | j) != 0);
         }
         if (leader) commit2(&bar, 3);
         __syncwarp();
@@ -144,17 +146,17 @@ static int run(int mode)
     CK(cudaMemcpy(dA, hA.data(), hA.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice));
     CK(cudaMemset(dSt, 0, 4)); CK(cudaMemset(dOut, 0xEE, 256 * (N + 16) * 4));
-    CK(cudaFuncSetAttribute(k2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_BYTES + B_BYTES));
+    CK(cudaFuncSetAttribute(k2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_BYTES + NBT * B_BYTES));
     const int shift = 3;
     for (int rep = 0; rep < (mode ? 2 : 1); ++rep) {
-        k2<N><<<2, 128, A_BYTES + B_BYTES>>>(dA, dB, dOut, mode, shift, dC, dSt);
+        k2<N><<<2, 128, A_BYTES + NBT * B_BYTES>>>(dA, dB, dOut, mode, shift, dC, dSt);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("N=%d mode=%d: CUDA error %s\n", N, mode, cudaGetErrorString(e)); return 2; }
     }
     int st; long long c[2];
     CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
-    if (mode == 1) {
-        printf("thr cta_group::2 M=256 N=%3d : %.1f cyc/mma (status %d)\n", N, (double)c[0] / (64 * 32), st);
+    if (mode >= 1) {
+        printf("%s cta_group::2 M=256 N=%3d : %.1f cyc/mma (status %d)\n", mode == 2 ? "thrb (8 B tiles in rotation)" : "thr", N, (double)c[0] / (64 * 32), st);
         return 0;
     }
     std::vector<int> out(256 * (N + 16));
@@ -184,7 +186,7 @@ int main(int argc, char **argv)
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
     printf("# %s  test=%s\n", p.name, t);
-    const int mode = !strcmp(t, "thr");
+    const int mode = !strcmp(t, "thr") ? 1 : !strcmp(t, "thrb") ? 2 : 0;
     run<32>(mode); run<64>(mode); run<96>(mode); run<128>(mode);
     return 0;
 }
