@@ -1,6 +1,8 @@
 // umma_probe2 -- does tcgen05.mma.cta_group::2 (CTA pair, M = 2 x 128) work with the fused kernel's
 // operand layouts, what does an instruction cost, and can cta_group::1 MMAs be mixed in on the same TMEM?
-// Not part of the product.   usage: umma_probe2 [num|thr|thrb]   (thrb: throughput with a different B tile for every MMA)
+// Not part of the product.   usage: umma_probe2 num | thr [flags] | thrb
+//   thr flags (sum): 2 a different B tile for every MMA (= thrb), 4 six accumulator regions in rotation, 8 the other
+//   warps of both CTAs drain TMEM (tcgen05.ld) meanwhile, 16 the other warps hammer shared memory (ld.shared) meanwhile
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -53,12 +55,13 @@ __device__ __forceinline__ void commit2(uint64_t *bar, uint32_t mask)
 // mode 0: numerics (one MMA, optional second cta_group::1 MMA on columns 128.. of each CTA)
 // mode 1: throughput (64 x 32 MMAs)
 template <int N>
-__global__ void __cluster_dims__(2, 1, 1) k2(const int8_t *gA, const int8_t *gB, int *out, int mode, int shift, long long *cycles, int *status)
+__global__ void __cluster_dims__(2, 1, 1) k2(const int8_t *gA, const int8_t *gB, int *out, int mode, int shift, long long *cycles, int *status, int flags)
 {
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sA = sm, *sB = sm + A_BYTES;
     __shared__ uint64_t bar;
     __shared__ uint32_t s_tmem;
+    __shared__ volatile int s_stop;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cta_rank();
     // A: each CTA its own 128 rows (CTA r uses global rows r*PX..); B: CTA r holds rows [r*N/2, (r+1)*N/2)
@@ -66,14 +69,14 @@ __global__ void __cluster_dims__(2, 1, 1) k2(const int8_t *gA, const int8_t *gB,
         const int plane = i / PX, px = i % PX;
         reinterpret_cast<int4 *>(sA)[i] = reinterpret_cast<const int4 *>(gA)[(rank * 2 + plane) * PX + px];
     }
-    for (int t = 0; t < (mode == 2 ? NBT : 1); ++t)
+    for (int t = 0; t < ((flags & 2) ? NBT : 1); ++t)
         for (int i = tid; i < N; i += blockDim.x) {      // i = kc * (N/2) + n
             const int kc = i / (N / 2), n = i % (N / 2);
             reinterpret_cast<int4 *>(sB + t * N * 16)[kc * (N / 2) + n] = reinterpret_cast<const int4 *>(gB)[(rank * (N / 2) + n) * 2 + kc];
         }
     fence_proxy_async_smem();
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc2(&s_tmem, 256);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); s_stop = 0; }
+    if (warp == 0) tmem_alloc2(&s_tmem, 512);
     fence_before_sync();
     __syncthreads();
     cluster_sync();
@@ -92,13 +95,26 @@ __global__ void __cluster_dims__(2, 1, 1) k2(const int8_t *gA, const int8_t *gB,
             for (int o = 0; o < 64; ++o)
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (leader) mma2_i8_ss(tm, ad + (uint64_t)((j * 5) % 60), bd + (uint64_t)(mode == 2 ? ((j * 3) % NBT) * N : 0), id, (o | j) != 0);
+                    if (leader) mma2_i8_ss(tm + ((flags & 4) ? (uint32_t)((j % 6) * 64) : 0u), ad + (uint64_t)((j * 5) % 60),
+                                           bd + (uint64_t)((flags & 2) ? ((j * 3) % NBT) * N : 0), id, (o | (j / 6)) != 0);
         }
         if (leader) commit2(&bar, 3);
         __syncwarp();
     }
+    long long side = 0;
+    if (mode == 1 && warp != 0 && (flags & 24)) {
+        uint32_t r[16], acc = 0;
+        while (!s_stop) {
+            if (flags & 8) { tmem_ld_x16(tm + ((uint32_t)(warp * 32) << 16) + 384 + (side & 3) * 16, r); tmem_ld_wait(); acc += r[0]; }
+            if (flags & 16) acc += reinterpret_cast<volatile uint32_t *>(sA)[(tid * 4 + side * 128) & (A_BYTES / 4 - 1)];
+            ++side;
+            if (mbar_try_wait(&bar, 0)) break;
+        }
+        if (acc == 0x12345678u) out[0] = (int)acc;
+    }
     const bool ok = mbar_wait(&bar, 0);
     t1 = clock64();
+    if (tid == 0) s_stop = 1;
     fence_after_sync();
     if (!ok && tid == 0) atomicOr(status, 1 << rank);
     if (rank == 0 && tid == 0) { cycles[0] = t1 - t0; }
@@ -130,11 +146,11 @@ __global__ void __cluster_dims__(2, 1, 1) k2(const int8_t *gA, const int8_t *gB,
     fence_before_sync();
     __syncthreads();
     cluster_sync();
-    if (warp == 0) tmem_dealloc2(tm, 256);
+    if (warp == 0) tmem_dealloc2(tm, 512);
 }
 
 template <int N>
-static int run(int mode)
+static int run(int mode, int flags = 0)
 {
     std::vector<int8_t> hA(2 * A_BYTES), hB(NMAX * 32);
     uint32_t s = 4242;
@@ -149,14 +165,14 @@ static int run(int mode)
     CK(cudaFuncSetAttribute(k2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_BYTES + NBT * B_BYTES));
     const int shift = 3;
     for (int rep = 0; rep < (mode ? 2 : 1); ++rep) {
-        k2<N><<<2, 128, A_BYTES + NBT * B_BYTES>>>(dA, dB, dOut, mode, shift, dC, dSt);
+        k2<N><<<2, 128, A_BYTES + NBT * B_BYTES>>>(dA, dB, dOut, mode, shift, dC, dSt, flags);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("N=%d mode=%d: CUDA error %s\n", N, mode, cudaGetErrorString(e)); return 2; }
     }
     int st; long long c[2];
     CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
     if (mode >= 1) {
-        printf("%s cta_group::2 M=256 N=%3d : %.1f cyc/mma (status %d)\n", mode == 2 ? "thrb (8 B tiles in rotation)" : "thr", N, (double)c[0] / (64 * 32), st);
+        printf("thr flags=%2d cta_group::2 M=256 N=%3d : %.1f cyc/mma (status %d)\n", flags, N, (double)c[0] / (64 * 32), st);
         return 0;
     }
     std::vector<int> out(256 * (N + 16));
@@ -186,7 +202,9 @@ int main(int argc, char **argv)
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
     printf("# %s  test=%s\n", p.name, t);
-    const int mode = !strcmp(t, "thr") ? 1 : !strcmp(t, "thrb") ? 2 : 0;
-    run<32>(mode); run<64>(mode); run<96>(mode); run<128>(mode);
+    const int mode = (!strcmp(t, "thr") || !strcmp(t, "thrb")) ? 1 : 0;
+    const int flags = !strcmp(t, "thrb") ? 2 : (argc > 2 ? atoi(argv[2]) : 0);
+    if (mode) run<16>(mode, flags);
+    run<32>(mode, flags); run<64>(mode, flags); run<96>(mode, flags); run<128>(mode, flags);
     return 0;
 }
