@@ -1,6 +1,6 @@
 // umma_probe2 -- does tcgen05.mma.cta_group::2 (CTA pair, M = 2 x 128) work with the fused kernel's
 // operand layouts, what does an instruction cost, and can cta_group::1 MMAs be mixed in on the same TMEM?
-// Not part of the product.   usage: umma_probe2 num | thr [flags] | thrb
+// Not part of the product.   usage: umma_probe2 num | thr [flags] | thrb | lat
 //   thr flags (sum): 2 a different B tile for every MMA (= thrb), 4 six accumulator regions in rotation, 8 the other
 //   warps of both CTAs drain TMEM (tcgen05.ld) meanwhile, 16 the other warps hammer shared memory (ld.shared) meanwhile
 #include <cstdint>
@@ -149,6 +149,82 @@ __global__ void __cluster_dims__(2, 1, 1) k2(const int8_t *gA, const int8_t *gB,
     if (warp == 0) tmem_dealloc2(tm, 512);
 }
 
+// lat: what one cross-CTA handshake costs.  Per round: CTA 0 issues one M = 256 MMA and a multicast commit; in each CTA one
+// lane spins on the local mbarrier; then every thread of the cluster goes through barrier.cluster arrive + wait.
+//   cycles[0] = issue -> CTA 0's own waiter sees the commit      (MMA execution + commit latency, same SM clock)
+//   cycles[1] = issue -> CTA 0 leaves the cluster barrier        (+ the partner's waiter seeing it + barrier latency)
+//   cycles[2] = barrier.cluster arrive + wait alone, all threads arriving together
+__global__ void __cluster_dims__(2, 1, 1) k_lat(const int8_t *gA, long long *cycles, int *status, int rounds)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sA = sm, *sB = sm + A_BYTES;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    __shared__ long long s_seen;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t rank = cta_rank();
+    for (int i = tid; i < (A_BYTES + B_BYTES) / 16; i += blockDim.x) reinterpret_cast<int4 *>(sm)[i] = reinterpret_cast<const int4 *>(gA)[i % 512];
+    fence_proxy_async_smem();
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc2(&s_tmem, 512);
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync();
+    fence_after_sync();
+    const uint32_t tm = s_tmem;
+    const uint64_t ad = smem_desc(smem_u32(sA), PLANE_B, 128), bd = smem_desc(smem_u32(sB), 8 * 16, 128);
+    const uint32_t id = idesc_i8(256, 16, 1, 1);
+    long long a0 = 0, a1 = 0, a2 = 0;
+    for (int r = 0; r < rounds; ++r) {
+        long long t0 = 0;
+        if (rank == 0 && warp == 0) {
+            const bool leader = elect_one();
+            t0 = clock64();
+            if (leader) { mma2_i8_ss(tm, ad, bd, id, 0); commit2(&bar, 3); }
+            __syncwarp();
+        }
+        if (warp == 1) {
+            if ((tid & 31) == 0) { if (!mbar_wait(&bar, r & 1)) atomicOr(status, 1 << rank); s_seen = clock64(); }
+            __syncwarp();
+        }
+        __syncthreads();
+        cluster_sync();
+        const long long t1 = clock64();
+        if (rank == 0 && tid == 0) { a0 += s_seen - t0; a1 += t1 - t0; }
+        __syncthreads();
+    }
+    for (int r = 0; r < rounds; ++r) {
+        const long long t0 = clock64();
+        cluster_sync();
+        a2 += clock64() - t0;
+    }
+    if (rank == 0 && tid == 0) { cycles[0] = a0 / rounds; cycles[1] = a1 / rounds; cycles[2] = a2 / rounds; }
+    fence_before_sync();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 0) tmem_dealloc2(tm, 512);
+}
+
+static int run_lat()
+{
+    std::vector<int8_t> hA(8192, 1);
+    int8_t *dA; int *dSt; long long *dC;
+    CK(cudaMalloc(&dA, hA.size())); CK(cudaMalloc(&dSt, 4)); CK(cudaMalloc(&dC, 32));
+    CK(cudaMemcpy(dA, hA.data(), hA.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemset(dSt, 0, 4));
+    CK(cudaFuncSetAttribute(k_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, A_BYTES + B_BYTES));
+    for (int rep = 0; rep < 2; ++rep) {
+        k_lat<<<2, 128, A_BYTES + B_BYTES>>>(dA, dC, dSt, 200);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("lat: CUDA error %s\n", cudaGetErrorString(e)); return 2; }
+    }
+    int st; long long c[3];
+    CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(c, dC, 24, cudaMemcpyDeviceToHost));
+    printf("lat cta_group::2: issue -> own waiter sees the multicast commit %lld cyc; issue -> out of the cluster barrier %lld cyc; "
+           "barrier.cluster arrive+wait alone %lld cyc (status %d)\n", c[0], c[1], c[2], st);
+    return 0;
+}
+
 template <int N>
 static int run(int mode, int flags = 0)
 {
@@ -202,6 +278,7 @@ int main(int argc, char **argv)
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
     printf("# %s  test=%s\n", p.name, t);
+    if (!strcmp(t, "lat")) return run_lat();
     const int mode = (!strcmp(t, "thr") || !strcmp(t, "thrb")) ? 1 : 0;
     const int flags = !strcmp(t, "thrb") ? 2 : (argc > 2 ? atoi(argv[2]) : 0);
     if (mode) run<16>(mode, flags);
