@@ -150,6 +150,12 @@ QV_API long long qv_launch_count(const qv_net *net);
    Conc1.conc, Conc2.conc in the reference (inference/qvrcnn.cu:183,202,218). */
 QV_API int qv_get_activation(qv_net *net, int which /*1,2,3*/, int8_t *host_out);
 
+/* Test hook, needs no GPU: what the host builds for the fused kernel from a static model image (Appendix B format) --
+   the shared-memory weight image, the per-phase tcgen05 operand table (for window base 0 / TMEM base 0) and the layout
+   and requantiser constants.  sizes[3] = capacities in elements on entry, actual element counts on return; a buffer that
+   is null or too small is not written.  tests/test_fused_tables.py emulates the kernel's dataflow on these. */
+QV_API int qv_debug_fused_tables(const void *model_image, size_t len, uint8_t *wimg, uint32_t *ops, int32_t *consts, size_t sizes[3]);
+
 /* ---- model-file converters ------------------------------------------------- */
 /* model_qfp_HWCN2NCHW_VECT_C   inference/qvrcnn.cu:558-585 */
 QV_API int qv_convert_model_hwcn_to_vect_c(const char *file_in, const char *file_out);

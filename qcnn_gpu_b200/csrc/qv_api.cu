@@ -251,6 +251,23 @@ int qv_load_static_para_mem(qv_net *net, const void *image, size_t len)
     return sync_model(net);
 }
 
+int qv_debug_fused_tables(const void *image, size_t len, uint8_t *wimg, uint32_t *ops, int32_t *consts, size_t sizes[3])
+{
+    if (!image || !sizes) { set_error("qv_debug_fused_tables: null argument"); return QV_ERR_ARG; }
+    ModelHost m;
+    int rc = parse_model_vect_c((const uint8_t *)image, len, m);
+    if (rc) return rc;
+    std::vector<uint8_t> w;
+    std::vector<uint32_t> o;
+    std::vector<int32_t> c;
+    fused_debug_tables(m, w, o, c);
+    if (wimg && sizes[0] >= w.size()) memcpy(wimg, w.data(), w.size());
+    if (ops && sizes[1] >= o.size()) memcpy(ops, o.data(), o.size() * sizeof(uint32_t));
+    if (consts && sizes[2] >= c.size()) memcpy(consts, c.data(), c.size() * sizeof(int32_t));
+    sizes[0] = w.size(); sizes[1] = o.size(); sizes[2] = c.size();
+    return QV_OK;
+}
+
 int qv_load_static_para(qv_net *net, const char *filename)
 {
     if (!net) { set_error("qv_load_static_para: null handle"); return QV_ERR_ARG; }

@@ -660,9 +660,11 @@ struct FusedModel {
 // Writes 16 K-bytes of row n, K-chunk j, of a B block laid out [2][NR][16].
 static void put_chunk(uint8_t *blk, int NR, int j, int n, const int8_t *src16) { memcpy(blk + ((size_t)j * NR + n) * 16, src16, 16); }
 
-FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
+// Everything of the model that is built on the host: the weight image (the B operands in their ring block sequences, the
+// biases) and the kernel-parameter constants (requantiser rows, C4 weights).  Returns whether the fast requantiser applies.
+static bool build_host_image(const ModelHost &m, std::vector<uint8_t> &img, FusedParams &P)
 {
-    std::vector<uint8_t> img(WIMG_BYTES, 0);
+    img.assign(WIMG_BYTES, 0);
     auto Wt = [&](int l, int k, int c, int r, int s) -> int8_t {
         const LayerShape &sh = kLayers[l];
         return m.L[l].w[(((size_t)k * sh.cin + c) * sh.k + r) * sh.k + s];
@@ -734,7 +736,6 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
             put_chunk(img.data() + OFF_W32 + (pl / 2) * T32, NR32, pl == 2 ? 1 : pl, ch, c16);
         }
     // ---- requantiser constants ---------------------------------------------------------------------
-    FusedModel *fm = new FusedModel();
     auto mkq = [&](int l, GroupQ &g) -> bool {
         const LayerHost &L = m.L[l];
         g.blu = L.blu; g.mul = L.mul; g.shift = L.shift; g.rbias = (1 << (L.shift - 1)) / L.mul;
@@ -744,11 +745,9 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
         g.M = ok ? (unsigned)((unsigned long long)L.mul << (24 - L.shift)) : 0u;
         return ok;
     };
-    FusedParams &P = fm->proto;
     bool fast = true;
     fast &= mkq(QV_C1, P.q1); fast &= mkq(QV_C2_2, P.q22); fast &= mkq(QV_C2_1, P.q21);
     fast &= mkq(QV_C3_1, P.q31); fast &= mkq(QV_C3_2, P.q32);
-    fm->fast = fast;
     int *bias = reinterpret_cast<int *>(img.data() + OFF_BIAS);
     auto addb = [&](int l, int dst0, const GroupQ &g) {
         for (int k = 0; k < kLayers[l].cout; ++k) bias[dst0 + k] = m.L[l].b[k] + (fast ? g.rbias : 0);
@@ -765,6 +764,36 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
                 for (int b = 0; b < 4; ++b) v |= (unsigned)(uint8_t)Wt(QV_C4, 0, 16 * pl + 4 * j + b, t / 3, t % 3) << (8 * b);
                 P.c4_w[(t * 3 + pl) * 4 + j] = (int)v;
             }
+    return fast;
+}
+
+// Test hook, no GPU involved: the structures the host builds for the kernel -- weight image, the per-phase MMA operand
+// table (for shared-memory window base 0 and TMEM base 0) and the constants -- so that a CPU emulation of the kernel's
+// dataflow can be checked against the oracle (tests/test_fused_tables.py).
+void fused_debug_tables(const ModelHost &m, std::vector<uint8_t> &wimg, std::vector<uint32_t> &ops, std::vector<int32_t> &consts)
+{
+    FusedParams P{};
+    const bool fast = build_host_image(m, wimg, P);
+    PhaseBases pb[N_PHASE];
+    FixedBases fb;
+    build_mma_bases(0, 0, pb, fb);
+    std::vector<PhaseOps> po(N_PHASE);
+    build_mma_ops(pb, fb, po.data());
+    ops.assign(reinterpret_cast<const uint32_t *>(po.data()), reinterpret_cast<const uint32_t *>(po.data() + N_PHASE));
+    consts = {WIMG_BYTES, SMEM_BYTES, OFF_A1, OFF_A2, OFF_IM, OFF_ZERO, OFF_IN, OFF_A3, PW, PLANE, A1_ROW, A2_ROW, IM_BYTES, IN_SLOTS,
+              IN_PITCH, WT, PIPE, TM_D1, TM_R22, TM_R21, TM_R31, TM_D32, N_PHASE, N_MMA, fast ? 1 : 0, P.c4_bias, P.c4_mul, P.c4_shift};
+    for (const GroupQ *g : {&P.q1, &P.q22, &P.q21, &P.q31, &P.q32})
+        for (int v : {g->hi, (int)g->M, g->blu, g->mul, g->shift, g->rbias}) consts.push_back(v);
+    consts.insert(consts.end(), P.bias, P.bias + BIAS_INTS);
+    consts.insert(consts.end(), P.c4_w, P.c4_w + 108);
+}
+
+FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
+{
+    std::vector<uint8_t> img;
+    FusedModel *fm = new FusedModel();
+    FusedParams &P = fm->proto;
+    fm->fast = build_host_image(m, img, P);
     cudaError_t e = cudaMalloc(&fm->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fm->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -1,6 +1,7 @@
 // Host-visible interface of the fused tcgen05 path (qv_fused.cu).
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "qv_internal.h"
@@ -18,5 +19,8 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
 // After the stream the kernel ran on has been synchronised: 0, or what a CTA reported (1 = an mbarrier wait timed
 // out, 2 = shared-memory / TMEM bases other than the operand table was built for); the report is cleared.
 int fused_take_failure(const FusedModel *fm);
+
+// Test hook (no GPU): weight image, per-phase MMA operand table (bases 0) and constants as the host builds them.
+void fused_debug_tables(const ModelHost &m, std::vector<uint8_t> &wimg, std::vector<uint32_t> &ops, std::vector<int32_t> &consts);
 
 }  // namespace qv
