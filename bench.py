@@ -116,6 +116,182 @@ def build_inputs(rank: int):
     return model, formats.write_model_vect_c(model), np.tile(anchor, (reps, 1, 1)), np.tile(ori, (reps, 1, 1))
 
 
+def copy_ceiling(torch, dist, world, nbytes, reps=6):
+    """What the host side of this box can move: every rank copies `nbytes` host->device and `nbytes` device->host between
+    pinned memory and HBM CONCURRENTLY (two streams, one cudaMemcpyAsync per copy), all ranks at once -- the traffic pattern of
+    the e2e step without any compute.  Returns aggregate GB/s each way (bytes of all ranks / slowest rank's time)."""
+    h_a = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d_b = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+
+    def once():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    gbs = world * nbytes * reps / float(dt.item()) / 1e9
+    return {"h2d_plus_d2h_concurrent_gbs_each_way": gbs, "per_gpu_gbs_each_way": gbs / world, "bytes_per_copy": nbytes, "reps": reps,
+            "how": "pinned <-> HBM, one cudaMemcpyAsync per copy, H2D and D2H on two streams, all ranks at once, no compute"}
+
+
+def run_config4(torch, dist, api, rank, world, local, steps=5, warmup=2):
+    """BASELINE config 4: QVRCNN QP=27, 240 frames of 3840x2160, frame-sharded (240/N per GPU, no collective), device
+    resident.  Bit-identity with one GPU: every rank's distinct frames and their outputs are gathered on rank 0, which runs
+    them alone; the tiled copies are compared on the rank that made them."""
+    from qcnn_gpu_b200.host import formats, shard, synth
+    qp, total, h, w, uniq = 27, 240, 2160, 3840, 2
+    f0, nf = shard.split(total, rank, world)
+    model = synth.make_model(0xC0FFEE + qp, qp)
+    image = formats.write_model_vect_c(model)
+    a, _ = synth.make_frames(0xC0FFEE + 4, uniq, h, w, first_frame=rank * uniq)
+    d_u = torch.from_numpy(a).cuda()
+    d_in = d_u.repeat((nf + uniq - 1) // uniq, 1, 1)[:nf].contiguous()
+    d_out = torch.empty_like(d_in)
+    net = api.QVRCNN(local, 8, 1, h, w)
+    net.load_static_para_mem(image)
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    run = lambda: net.forward_frames_device(d_in.data_ptr(), d_out.data_ptr(), nf, st.cuda_stream)
+    for _ in range(warmup):
+        run()
+    net.synchronize(st.cuda_stream)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        run()
+    e1.record(st)
+    net.synchronize(st.cuda_stream)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    # every copy of a distinct frame gave the same output (checked where it was computed) ...
+    ok_local = all(bool(torch.equal(d_out[j], d_out[j % uniq])) for j in range(uniq, nf))
+    flag = torch.tensor([1 if ok_local else 0], dtype=torch.int64, device="cuda")
+    g_in = [torch.empty_like(d_u) for _ in range(world)]
+    g_out = [torch.empty_like(d_u) for _ in range(world)]
+    mine_out = d_out[:uniq].contiguous()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_gather(g_in, d_u)
+        dist.all_gather(g_out, mine_out)
+    else:
+        g_in, g_out = [d_u], [mine_out]
+    block = None
+    if rank == 0:
+        # ... and the distinct frames of every rank, run by rank 0 alone, give what the ranks got
+        solo_in = torch.cat(g_in)
+        solo_out = torch.empty_like(solo_in)
+        net.forward_frames_device(solo_in.data_ptr(), solo_out.data_ptr(), solo_in.shape[0], st.cuda_stream)
+        net.synchronize(st.cuda_stream)
+        same = bool(torch.equal(solo_out, torch.cat(g_out))) and bool(flag.item() == 1)
+        t = float(ms.item()) / steps
+        block = {"workload": "config4: QVRCNN QP=27, 240x3840x2160 frames, frame-sharded (%d per GPU)" % nf, "n_gpus": world,
+                 "Mpixel_per_s": total * h * w / (t * 1e-3) / 1e6, "ms_per_step": t, "steps": steps, "scaling": "strong",
+                 "bit_identical_to_1gpu": same, "bytes_exchanged_per_step": 0, "collectives_in_timed_region": 0,
+                 "distinct_frames_per_gpu": uniq}
+    del net, d_in, d_out
+    torch.cuda.empty_cache()
+    return block
+
+
+def run_config5(torch, dist, api, rank, world, local, steps=20, warmup=3):
+    """BASELINE config 5: QVRCNN QP=22, ONE 7680x4320 frame cut into N horizontal strips, one per GPU.  Each GPU keeps only
+    its own rows; the fused kernel reads the 6 halo rows either side out of the neighbour GPUs' HBM (peer-mapped through CUDA
+    IPC, NVLink), ordered by sequence words the kernels write and poll themselves: no NCCL call and no host
+    synchronisation between frames (qv_strip_forward).  The check uploads a DIFFERENT frame for each of two further
+    steps, alternating the two input slots, and rank 0 recomputes those frames alone."""
+    from qcnn_gpu_b200.host import formats, multi_gpu, shard, synth
+    qp, h, w = 22, 4320, 7680
+    model = synth.make_model(0xC0FFEE + qp, qp)
+    image = formats.write_model_vect_c(model)
+    sr = multi_gpu.StripRank(api, shard, local, image, h, w, rank, world, dist)
+    net, y0, y1 = sr.net, sr.y0, sr.y1
+    st = torch.cuda.Stream()
+    sp = st.cuda_stream
+    a, _ = synth.make_frames(0xC0FFEE + 5, 1, h, w, rows=(y0, y1))
+    d_out = torch.empty((y1 - y0, w), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    net.strip_load(0, a[0], sp)
+    l0 = net.launch_count()
+    for _ in range(warmup):
+        net.strip_forward(0, d_out.data_ptr(), sp)
+    net.synchronize(sp)
+    per_step_launches = (net.launch_count() - l0) / max(1, warmup)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        net.strip_forward(0, d_out.data_ptr(), sp)
+    e1.record(st)
+    net.synchronize(sp)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    # check: further, different frames, alternating the input slots
+    n_chk = 2
+    outs, fks = [], []
+    for k in range(n_chk):
+        fk = synth.make_frames(0xC0FFEE + 5, 1, h, w, first_frame=1 + k, rows=(y0, y1))[0][0]
+        fks.append(fk)
+        net.strip_load((k + 1) & 1, fk, sp)
+        net.strip_forward((k + 1) & 1, d_out.data_ptr(), sp)
+        with torch.cuda.stream(st):
+            outs.append(d_out.clone())
+    net.synchronize(sp)
+    mine = torch.stack(outs)                                         # [n_chk, rows, w]
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        rows = [shard.split(h, r, world)[1] for r in range(world)]
+        parts = [torch.empty((n_chk, rows[r], w), dtype=torch.uint8, device="cuda") for r in range(world)]
+        # rows per rank may differ by one: gather through rank 0 with point-to-point copies (outside the timed region)
+        if rank == 0:
+            parts[0] = mine
+            for r in range(1, world):
+                dist.recv(parts[r], src=r)
+        else:
+            dist.send(mine, dst=0)
+    else:
+        parts = [mine]
+    block = None
+    if rank == 0:
+        got = torch.cat(parts, dim=1)
+        full = np.stack(fks) if world == 1 else np.concatenate([synth.make_frames(0xC0FFEE + 5, 1, h, w, first_frame=1 + k)[0] for k in range(n_chk)])
+        solo = api.QVRCNN(local, 1, 1, h, w)
+        solo.load_static_para_mem(image)
+        d_full = torch.from_numpy(full).cuda()
+        d_want = torch.empty_like(d_full)
+        solo.forward_frames_device(d_full.data_ptr(), d_want.data_ptr(), n_chk, sp)
+        solo.synchronize(sp)
+        t = float(ms.item()) / steps
+        halo_bytes = (2 * world - 2) * shard.HALO * w
+        block = {"workload": "config5: QVRCNN QP=22, one 7680x4320 frame in %d horizontal strip(s)" % world, "n_gpus": world,
+                 "Mpixel_per_s": h * w / (t * 1e-3) / 1e6, "ms_per_frame": t, "steps": steps, "scaling": "strong",
+                 "bit_identical_to_1gpu": bool(torch.equal(got, d_want)), "distinct_frames_checked": n_chk,
+                 "halo": "6 rows each way read by the fused kernel from the neighbour GPU's HBM (peer-mapped, CUDA IPC, NVLink)" if world > 1 else "none (one strip)",
+                 "bytes_exchanged_per_step": halo_bytes, "nccl_calls_between_frames": 0, "kernel_launches_per_step_per_gpu": per_step_launches}
+        del solo
+    if world > 1:
+        dist.barrier()
+    net.strip_release()
+    del net
+    torch.cuda.empty_cache()
+    return block
+
+
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "qcnn_ref_witness")
 
 
@@ -197,6 +373,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "fused", "layered"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-steps", type=int, default=320, help="back-to-back steps of the `sustained` block (>= 2 s)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config4 / config5 blocks")
     ap.add_argument("--reference-kind", default="auto", choices=["auto", "cpu"],
                     help="--impl reference: auto = the real reference (cuDNN) when it can run, cpu = the CPU port only")
     args = ap.parse_args()
@@ -239,7 +418,8 @@ def main():
     d_in = h_in.cuda()
     d_ori = torch.from_numpy(ori).cuda()
     d_out = torch.empty_like(d_in)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                 # an explicit stream: launches and the timing events share it
+    torch.cuda.synchronize()
     npx = FRAMES * H * W
 
     def step_device():
@@ -260,16 +440,47 @@ def main():
     for i in range(args.steps):
         step_device()
         evs[i + 1].record(stream)
+    net.synchronize(stream.cuda_stream)          # also surfaces a failure a CTA reported
     barrier()
     launches = net.launch_count() - l0
     sampler.stop()
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
 
+    # The steady state: the default region above is ~0.2 s, over before the board's power reading catches up; SUSTAINED_STEPS
+    # back-to-back steps (>= 2 s) with their own clock sample show the operating point under the 1000 W cap.
+    sustained = None
+    if not args.no_sustained:
+        s2 = ClockSampler(local)
+        s2.start()
+        t_s = time.perf_counter()
+        while not s2.samples and time.perf_counter() - t_s < 8.0:
+            time.sleep(0.05)
+        barrier()
+        n_sus = max(args.sustained_steps, 1)
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        es[0].record(stream)
+        for i in range(n_sus):
+            if i == n_sus // 2:
+                s2.samples.clear()               # clocks of the second half only
+                es[1].record(stream)
+            step_device()
+        es[2].record(stream)
+        net.synchronize(stream.cuda_stream)
+        barrier()
+        s2.stop()
+        sus = torch.tensor([es[0].elapsed_time(es[2]), es[1].elapsed_time(es[2])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sus, op=dist.ReduceOp.MAX)
+        sustained = {"steps": n_sus, "seconds": float(sus[0].item()) * 1e-3, "ms_per_step": float(sus[0].item()) / n_sus,
+                     "ms_per_step_second_half": float(sus[1].item()) / (n_sus - n_sus // 2), "clocks_second_half": s2.summary()}
+
     # PSNR report + exact SSE (outside the timed region); the one collective of the job
     acc = torch.zeros(2, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     api.sse_device(d_in.data_ptr(), d_ori.data_ptr(), npx, acc[0:1].data_ptr(), stream.cuda_stream)
     api.sse_device(d_out.data_ptr(), d_ori.data_ptr(), npx, acc[1:2].data_ptr(), stream.cuda_stream)
+    stream.synchronize()
     tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
@@ -293,6 +504,11 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_mpx = world * npx * e2e_steps / float(e2e_s.item()) / 1e6
     same = bool(torch.equal(h_out.cuda(), d_out))
+    ceiling = copy_ceiling(torch, dist, world, npx)
+    cfg4 = cfg5 = None
+    if not args.no_extra_configs and net.get_impl() == api.IMPL_FUSED:
+        cfg4 = run_config4(torch, dist, api, rank, world, local)
+        cfg5 = run_config5(torch, dist, api, rank, world, local)
 
     # The reference driver's own call pattern (inference/kernel.cu:91-97: per frame load_data, forward_blu, D2H of x_rec),
     # one 1920x1080 frame per call through the drop-in surface -- what a user who only relinks the driver gets.
@@ -345,6 +561,8 @@ def main():
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": npx, "d2h_bytes_per_step": npx,
                     "api": "qv_forward_frames_host (pinned host in/out)", "bit_identical_to_device_path": same,
+                    "copy_ceiling": ceiling, "copy_gbs_each_way": e2e_mpx * 1e6 / 1e9,
+                    "frac_of_copy_ceiling": e2e_mpx * 1e6 / 1e9 / ceiling["h2d_plus_d2h_concurrent_gbs_each_way"],
                     "numa": numa_info, "reference_call_pattern": per_frame},
             "roofline": {"bound": "tensor", "achieved": tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": tops / int8_peak,
                          "traffic": ncu_traffic(), "peak_source": "2 x bf16_tflops (burst), " + peaks["source"],
@@ -356,6 +574,16 @@ def main():
             "psnr": {"before_net": psnr_before, "after_quantized_net": psnr_after},
             "step_ms": [round(x, 3) for x in step_ms],
         }
+        if sustained:
+            t_s = npx / (sustained["ms_per_step_second_half"] * 1e-3) * OPS_PER_PIXEL / 1e12
+            sustained.update({"Mpixel_per_s": world * npx / (sustained["ms_per_step"] * 1e-3) / 1e6,
+                              "tops_per_gpu_second_half": t_s, "frac_of_2x_bf16_sustained": t_s / (2.0 * peaks["bf16_sustained"]),
+                              "frac_of_2x_bf16_burst": t_s / int8_peak, "frac_of_nominal_4500": t_s / 4500.0})
+            line["sustained"] = sustained
+        if cfg4:
+            line["config4"] = cfg4
+        if cfg5:
+            line["config5"] = cfg5
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle
             from qcnn_gpu_b200.host import formats

@@ -126,9 +126,47 @@ QV_API int qv_forward_frames_device(qv_net *net, const uint8_t *d_in, uint8_t *d
    `in_rows` rows (the strip plus up to 6 halo rows each side); rows [out_row0, out_row1) are
    written to d_out (whose first row is out_row0).  Activations outside the IMAGE are zero
    (each layer's own SAME padding, inference/cnn.cu:44-49); rows outside the strip but inside
-   the image are recomputed from the halo. */
+   the image are recomputed from the halo.  (The caller has gathered the halo rows; qv_strip_* below
+   is the variant in which the kernel reads them from the neighbour GPUs' memory.) */
 QV_API int qv_forward_rows_device(qv_net *net, const uint8_t *d_in, int img_height, int in_row0, int in_rows,
                                   uint8_t *d_out, int out_row0, int out_row1, void *cuda_stream);
+
+/* Synchronises `cuda_stream` (NULL = the handle's own stream) and reports what the kernels that ran on it found:
+   QV_ERR_CUDA if a CTA of the fused kernel gave up on a wait (the output of that launch is not valid), QV_OK otherwise.
+   The asynchronous entry points (a non-NULL cuda_stream) cannot report this themselves; a NULL cuda_stream names the
+   handle's own stream and makes the call synchronous -- to run on the legacy default stream pass cudaStreamLegacy. */
+QV_API int qv_synchronize(qv_net *net, void *cuda_stream);
+
+/* ---- one very large frame over several GPUs: horizontal strips, halo rows read over NVLink ------------
+   The reference runs on device 0 only (inference/kernel.cu:86); forward_blu's receptive field is 2+2+1+1 = 6 rows, so
+   a GPU that owns image rows [row0, row1) needs 6 more rows from the GPU above and 6 from the GPU below.  They are
+   never copied: every handle keeps its rows in a block of its own device memory which the two neighbours MAP (same
+   process: CUDA peer access; another process: CUDA IPC) and the fused kernel's input stage loads the halo rows straight
+   from the neighbour's HBM.  Ordering is by sequence numbers in the same block, written and polled by the kernels
+   themselves (system-scope release / acquire): no collective, no host synchronisation between frames.  All handles of a
+   frame must make the same sequence of qv_strip_forward calls.  Fused path only.
+
+     each GPU:  qv_create(gpu, 1, 1, rows, W) ; load model ; qv_strip_setup(net, H, row0, row1) ; qv_strip_export(net, &d)
+     exchange the 192-byte descriptors once (threads: a shared array; processes: any byte transport)
+     each GPU:  qv_strip_attach(net, QV_STRIP_ABOVE, &d[above]) ; qv_strip_attach(net, QV_STRIP_BELOW, &d[below])
+     per frame k: qv_strip_load(net, k & 1, host_rows, st) ; qv_strip_forward(net, k & 1, d_out, st)                     */
+typedef struct { unsigned char opaque[192]; } qv_strip_desc;
+enum { QV_STRIP_ABOVE = 0, QV_STRIP_BELOW = 1 };
+/* This handle owns image rows [row0, row1) of an img_height x width frame (width = the handle's). */
+QV_API int qv_strip_setup(qv_net *net, int img_height, int row0, int row1);
+QV_API int qv_strip_export(qv_net *net, qv_strip_desc *out);
+/* Maps the neighbour's block.  Fails if the rows are not adjacent, or if the neighbour holds fewer than 6 rows. */
+QV_API int qv_strip_attach(qv_net *net, int side, const qv_strip_desc *neighbour);
+/* Device pointer of input slot 0 / 1 ((row1-row0) * width bytes) for callers that fill it on the device. */
+QV_API int qv_strip_input(qv_net *net, int slot, void **d_rows);
+/* Before overwriting a slot: waits (on the stream) until both neighbours have finished the step that read it. */
+QV_API int qv_strip_acquire(qv_net *net, int slot, void *cuda_stream);
+/* qv_strip_acquire + H2D copy of this GPU's rows into the slot (InputLayer::load, inference/cnn.cu:439-443). */
+QV_API int qv_strip_load(qv_net *net, int slot, const uint8_t *host_rows, void *cuda_stream);
+/* forward_blu on this GPU's rows of the frame in `slot`; rows [row0, row1) of the reconstruction go to d_out. */
+QV_API int qv_strip_forward(qv_net *net, int slot, uint8_t *d_out, void *cuda_stream);
+/* Unmaps the neighbours and frees the block (all GPUs must be idle). */
+QV_API int qv_strip_release(qv_net *net);
 
 /* Explicit device-pointer accessor for drivers that, like the reference's, read the object's
    buffers directly (`qvrcnn1.I1.x_rec`, inference/kernel.cu:96; InputLayer::x / x_rec,

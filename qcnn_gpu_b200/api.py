@@ -31,8 +31,20 @@ ABI_SYMBOLS = (
     "qv_set_impl", "qv_get_impl", "qv_launch_count", "qv_get_activation",
     "qv_convert_model_hwcn_to_vect_c", "qv_yuv_read_luma", "qv_yuv_read_frame", "qv_yuv_write_recon",
     "qv_psnr", "qv_psnr_from_sse", "qv_solve_quant_params", "qv_write_quant_params_cpp", "qv_quantize_layer",
-    "qv_debug_fused_tables",
+    "qv_debug_fused_tables", "qv_synchronize",
+    "qv_strip_setup", "qv_strip_export", "qv_strip_attach", "qv_strip_input", "qv_strip_acquire", "qv_strip_load",
+    "qv_strip_forward", "qv_strip_release",
 )
+
+CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy: names the legacy default stream explicitly (NULL = "the handle's own stream")
+STRIP_ABOVE, STRIP_BELOW = 0, 1
+STRIP_DESC_BYTES = 192
+
+
+def stream_arg(stream: int):
+    """A cudaStream_t for the ABI from a torch `cuda_stream` integer: torch reports the legacy default stream as 0, which
+    the ABI reads as "use the handle's private stream, synchronously" -- name it explicitly instead."""
+    return CUDA_STREAM_LEGACY if not stream else stream
 
 
 class QVError(RuntimeError):
@@ -92,6 +104,15 @@ def lib():
         L.qv_solve_quant_params.argtypes = [vp, vp, vp]
         L.qv_write_quant_params_cpp.argtypes = [cp, vp]
         L.qv_quantize_layer.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_double, C.c_double, vp, vp]
+        L.qv_synchronize.argtypes = [vp, vp]
+        L.qv_strip_setup.argtypes = [vp, i32, i32, i32]
+        L.qv_strip_export.argtypes = [vp, vp]
+        L.qv_strip_attach.argtypes = [vp, i32, vp]
+        L.qv_strip_input.argtypes = [vp, i32, C.POINTER(vp)]
+        L.qv_strip_acquire.argtypes = [vp, i32, vp]
+        L.qv_strip_load.argtypes = [vp, i32, vp, vp]
+        L.qv_strip_forward.argtypes = [vp, i32, vp, vp]
+        L.qv_strip_release.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -191,6 +212,41 @@ class QVRCNN:
                             out_row0: int, out_row1: int, stream: int = 0) -> None:
         _check(lib().qv_forward_rows_device(self._h, d_in, img_height, in_row0, in_rows, d_out, out_row0,
                                             out_row1, stream or None))
+
+    def synchronize(self, stream: int = 0) -> None:
+        """Synchronises the stream (0 = the handle's own) and raises if a kernel on it reported a failure."""
+        _check(lib().qv_synchronize(self._h, stream or None))
+
+    # -- one frame over several GPUs: strips with peer-mapped halo rows (qv_strip_*) -----------
+    def strip_setup(self, img_height: int, row0: int, row1: int) -> None:
+        _check(lib().qv_strip_setup(self._h, img_height, row0, row1))
+
+    def strip_export(self) -> bytes:
+        buf = C.create_string_buffer(STRIP_DESC_BYTES)
+        _check(lib().qv_strip_export(self._h, buf))
+        return buf.raw
+
+    def strip_attach(self, side: int, desc: bytes) -> None:
+        assert len(desc) == STRIP_DESC_BYTES
+        _check(lib().qv_strip_attach(self._h, side, C.create_string_buffer(desc, STRIP_DESC_BYTES)))
+
+    def strip_input(self, slot: int) -> int:
+        p = C.c_void_p()
+        _check(lib().qv_strip_input(self._h, slot, C.byref(p)))
+        return int(p.value)
+
+    def strip_acquire(self, slot: int, stream: int = 0) -> None:
+        _check(lib().qv_strip_acquire(self._h, slot, stream or None))
+
+    def strip_load(self, slot: int, rows_u8: np.ndarray, stream: int = 0) -> None:
+        x = np.ascontiguousarray(rows_u8, np.uint8)
+        _check(lib().qv_strip_load(self._h, slot, x.ctypes.data, stream or None))
+
+    def strip_forward(self, slot: int, d_out: int, stream: int = 0) -> None:
+        _check(lib().qv_strip_forward(self._h, slot, d_out, stream or None))
+
+    def strip_release(self) -> None:
+        _check(lib().qv_strip_release(self._h))
 
     # -- controls ---------------------------------------------------------------------------
     def set_impl(self, impl: int) -> None:

@@ -3,13 +3,17 @@
 // variants the multi-GPU driver uses.  Mirrors class qvrcnn (inference/qvrcnn.cuh:25-59,
 // inference/qvrcnn.cu:4-68,168-242) and the hot loop of testqvrcnn (inference/kernel.cu:86-97).
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <random>
 #include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include <cuda_runtime.h>
 
@@ -28,7 +32,52 @@ using namespace qv;
         }                                                                                   \
     } while (0)
 
+// ---- spatial strips over several GPUs ---------------------------------------------------------
+// One cudaMalloc'ed block per handle: a 256-byte header (published / completed sequence numbers, CTA counter) and two
+// input slots holding this GPU's rows of the frame.  The block is what neighbours map (same process: peer access;
+// other process: CUDA IPC) and read their 6 halo rows from, straight out of this GPU's HBM over NVLink.
+namespace {
+constexpr int STRIP_HALO = 6;                   // receptive-field radius of the net: 2 + 2 + 1 + 1 rows
+constexpr size_t STRIP_HDR = 256, STRIP_PUB = 0, STRIP_DONE = 64, STRIP_CTR = 128;
+constexpr uint32_t STRIP_MAGIC = 0x51565354u;   // "QVST"
+struct StripDescImpl {                          // the content of qv_strip_desc
+    uint32_t magic;
+    int32_t dev, row0, row1, width, img_h;
+    uint64_t nonce;                             // identifies the exporting process
+    uint64_t base, slot_off, slot_stride;
+    cudaIpcMemHandle_t ipc;
+    char pci[16];                               // PCI bus id of the device: device ordinals differ between processes
+};
+static_assert(sizeof(StripDescImpl) <= sizeof(qv_strip_desc), "qv_strip_desc too small");
+struct StripPeer {
+    bool attached = false, ipc = false, same_device = false;
+    uint8_t *base = nullptr;
+    StripDescImpl d{};
+};
+struct StripState {
+    bool on = false;
+    int img_h = 0, row0 = 0, row1 = 0;
+    uint8_t *block = nullptr;
+    size_t slot_stride = 0;
+    uint32_t seq = 0, slot_seq[2] = {0, 0};
+    StripPeer peer[2];                          // QV_STRIP_ABOVE, QV_STRIP_BELOW
+};
+// Strip-mode handles of this process per device.  A handle that is alone on its device lets the fused kernel itself wait
+// for the neighbours' rows; with several strips on one device a kernel spinning on every SM could keep the very kernel it
+// waits for from being scheduled, so those handles wait with a one-warp kernel on the stream instead.
+std::atomic<int> g_strip_handles[64];
+uint64_t process_nonce()
+{
+    static const uint64_t n = [] {
+        std::random_device rd;
+        return ((uint64_t)rd() << 32) ^ (uint64_t)rd() ^ ((uint64_t)getpid() << 17);
+    }();
+    return n;
+}
+}  // namespace
+
 struct qv_net {
+    StripState strip;
     int dev = 0, batch = 0, H = 0, W = 0;
     cudaStream_t st = nullptr;
     cudaStream_t pst[2] = {nullptr, nullptr};      // pipeline slots of qv_forward_frames_host
@@ -225,6 +274,7 @@ int qv_destroy(qv_net *net)
     if (!net) return QV_OK;
     cudaSetDevice(net->dev);
     if (net->st) cudaStreamSynchronize(net->st);
+    qv_strip_release(net);
     free_layered(net);
     if (net->fm) fused_free(net->fm);
     cudaFree(net->d_x); cudaFree(net->d_rec);
@@ -341,7 +391,8 @@ static int kernel_report(qv_net *net)
     const int f = net->fm ? fused_take_failure(net->fm) : 0;
     if (!f) return QV_OK;
     set_error(f == 2 ? "fused kernel: a CTA saw other shared-memory / TMEM bases than the operand table was built for"
-                     : "fused kernel: an mbarrier wait timed out (the frame data of this call is not valid)");
+              : f == 3 ? "strip mode: a neighbour GPU's rows were never published (the frame data of this call is not valid)"
+                       : "fused kernel: an mbarrier wait timed out (the frame data of this call is not valid)");
     return QV_ERR_CUDA;
 }
 
@@ -385,36 +436,254 @@ int qv_forward_rows_device(qv_net *net, const uint8_t *d_in, int img_height, int
                            int out_row0, int out_row1, void *cuda_stream)
 {
     if (!net || !d_in || !d_out) { set_error("qv_forward_rows_device: null argument"); return QV_ERR_ARG; }
-    // The net's receptive-field radius is 2+2+1+1 = 6 rows: treating the [in_row0, in_row0+in_rows)
-    // window as an image of its own is exact for every output row that is >= 6 rows away from a
-    // window edge, or whose window edge IS the image edge (where zero padding is the truth).
+    // The net's receptive-field radius is 2+2+1+1 = 6 rows: every output row needs the input rows within 6 of it that
+    // lie inside the image; outside the image every layer pads its own input with zeros (inference/cnn.cu:44-49).
     const int in_row1 = in_row0 + in_rows;
     if (img_height < 1 || in_row0 < 0 || in_rows < 1 || in_row1 > img_height || out_row0 < in_row0 || out_row1 > in_row1 ||
         out_row0 > out_row1) { set_error("qv_forward_rows_device: inconsistent row ranges"); return QV_ERR_ARG; }
-    if ((in_row0 != 0 && out_row0 - in_row0 < 6) || (in_row1 != img_height && in_row1 - out_row1 < 6)) {
+    if ((in_row0 != 0 && out_row0 - in_row0 < STRIP_HALO) || (in_row1 != img_height && in_row1 - out_row1 < STRIP_HALO)) {
         set_error("qv_forward_rows_device: need 6 halo rows on every interior strip edge");
         return QV_ERR_ARG;
     }
     int rc = set_device(net);
     if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : net->st;
-    const size_t W = net->W, need = (size_t)in_rows * W;
-    if ((size_t)in_rows * W > (size_t)net->batch * net->H * net->W && net->impl == QV_IMPL_LAYERED) {
-        set_error("qv_forward_rows_device: window larger than the handle's geometry");
+    const size_t W = net->W;
+    const bool fused_path = net->impl == QV_IMPL_FUSED || (net->impl == QV_IMPL_AUTO && net->fm);
+    if (fused_path) {
+        // the fused kernel takes the window as what it is: rows [in_row0, in_row1) of an img_height-row image, of which it
+        // computes and writes exactly [out_row0, out_row1) -- no scratch frame, no copy
+        if (!net->uploaded || !net->fm) { set_error("forward called before a complete model (weights + quant params) was loaded"); return QV_ERR_STATE; }
+        FusedRows fr;
+        fr.own0 = in_row0; fr.own1 = in_row1; fr.out0 = out_row0; fr.out1 = out_row1;
+        QV_CUDA(fused_forward(net->fm, d_in, d_out, 1, img_height, net->W, st, &net->launches, &fr));
+    } else {
+        // layered path: the window is run as an image of its own (exact for rows >= 6 away from an interior window edge),
+        // then the asked-for rows are copied out
+        const size_t need = (size_t)in_rows * W;
+        if (need > (size_t)net->batch * net->H * net->W) {
+            set_error("qv_forward_rows_device: window larger than the handle's geometry");
+            return QV_ERR_ARG;
+        }
+        if (net->rows_tmp_bytes < need) {
+            QV_CUDA(cudaStreamSynchronize(st));
+            cudaFree(net->d_rows_tmp);
+            net->d_rows_tmp = nullptr; net->rows_tmp_bytes = 0;
+            QV_CUDA(cudaMalloc(&net->d_rows_tmp, need));
+            net->rows_tmp_bytes = need;
+        }
+        rc = run_forward(net, d_in, net->d_rows_tmp, 1, in_rows, net->W, st);
+        if (rc) return rc;
+        QV_CUDA(cudaMemcpyAsync(d_out, net->d_rows_tmp + (size_t)(out_row0 - in_row0) * W, (size_t)(out_row1 - out_row0) * W,
+                                cudaMemcpyDeviceToDevice, st));
+    }
+    if (!cuda_stream) { QV_CUDA(cudaStreamSynchronize(st)); return kernel_report(net); }
+    return QV_OK;
+}
+
+int qv_synchronize(qv_net *net, void *cuda_stream)
+{
+    if (!net) { set_error("qv_synchronize: null handle"); return QV_ERR_ARG; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    QV_CUDA(cudaStreamSynchronize(cuda_stream ? (cudaStream_t)cuda_stream : net->st));
+    return kernel_report(net);
+}
+
+// ---- strips: setup / export / attach / load / forward -------------------------------------------------------------
+static void strip_detach(qv_net *net)
+{
+    for (StripPeer &p : net->strip.peer) {
+        if (p.attached && p.ipc && p.base) cudaIpcCloseMemHandle(p.base);
+        p = StripPeer{};
+    }
+}
+
+int qv_strip_release(qv_net *net)
+{
+    if (!net) { set_error("qv_strip_release: null handle"); return QV_ERR_ARG; }
+    if (!net->strip.on) return QV_OK;
+    cudaSetDevice(net->dev);
+    cudaStreamSynchronize(net->st);
+    strip_detach(net);
+    cudaFree(net->strip.block);
+    net->strip = StripState{};
+    if (net->dev >= 0 && net->dev < 64) g_strip_handles[net->dev].fetch_sub(1);
+    return QV_OK;
+}
+
+int qv_strip_setup(qv_net *net, int img_height, int row0, int row1)
+{
+    if (!net) { set_error("qv_strip_setup: null handle"); return QV_ERR_ARG; }
+    if (img_height < 1 || row0 < 0 || row1 <= row0 || row1 > img_height) { set_error("qv_strip_setup: rows [%d, %d) of %d", row0, row1, img_height); return QV_ERR_ARG; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    qv_strip_release(net);
+    StripState &S = net->strip;
+    S.img_h = img_height; S.row0 = row0; S.row1 = row1;
+    S.slot_stride = ((size_t)(row1 - row0) * net->W + 255) / 256 * 256;
+    QV_CUDA(cudaMalloc(&S.block, STRIP_HDR + 2 * S.slot_stride));
+    QV_CUDA(cudaMemset(S.block, 0, STRIP_HDR));
+    QV_CUDA(cudaDeviceSynchronize());
+    S.on = true;
+    if (net->dev >= 0 && net->dev < 64) g_strip_handles[net->dev].fetch_add(1);
+    return QV_OK;
+}
+
+int qv_strip_export(qv_net *net, qv_strip_desc *out)
+{
+    if (!net || !out) { set_error("qv_strip_export: null argument"); return QV_ERR_ARG; }
+    if (!net->strip.on) { set_error("qv_strip_export: qv_strip_setup has not been called"); return QV_ERR_STATE; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    StripDescImpl d{};
+    d.magic = STRIP_MAGIC; d.dev = net->dev; d.row0 = net->strip.row0; d.row1 = net->strip.row1; d.width = net->W; d.img_h = net->strip.img_h;
+    d.nonce = process_nonce();
+    d.base = (uint64_t)(uintptr_t)net->strip.block; d.slot_off = STRIP_HDR; d.slot_stride = net->strip.slot_stride;
+    QV_CUDA(cudaIpcGetMemHandle(&d.ipc, net->strip.block));
+    QV_CUDA(cudaDeviceGetPCIBusId(d.pci, (int)sizeof(d.pci), net->dev));
+    memset(out, 0, sizeof(*out));
+    memcpy(out, &d, sizeof(d));
+    return QV_OK;
+}
+
+int qv_strip_attach(qv_net *net, int side, const qv_strip_desc *neighbour)
+{
+    if (!net || !neighbour || (side != QV_STRIP_ABOVE && side != QV_STRIP_BELOW)) { set_error("qv_strip_attach: bad argument"); return QV_ERR_ARG; }
+    StripState &S = net->strip;
+    if (!S.on) { set_error("qv_strip_attach: qv_strip_setup has not been called"); return QV_ERR_STATE; }
+    StripDescImpl d;
+    memcpy(&d, neighbour, sizeof(d));
+    if (d.magic != STRIP_MAGIC) { set_error("qv_strip_attach: not a strip descriptor"); return QV_ERR_ARG; }
+    if (d.width != net->W || d.img_h != S.img_h) { set_error("qv_strip_attach: the neighbour's frame is %dx%d, this one %dx%d", d.width, d.img_h, net->W, S.img_h); return QV_ERR_ARG; }
+    if (side == QV_STRIP_ABOVE ? d.row1 != S.row0 : d.row0 != S.row1) {
+        set_error("qv_strip_attach: rows [%d, %d) are not adjacent %s rows [%d, %d)", d.row0, d.row1, side == QV_STRIP_ABOVE ? "above" : "below", S.row0, S.row1);
         return QV_ERR_ARG;
     }
-    if (net->rows_tmp_bytes < need) {
-        QV_CUDA(cudaStreamSynchronize(st));
-        cudaFree(net->d_rows_tmp);
-        net->d_rows_tmp = nullptr; net->rows_tmp_bytes = 0;
-        QV_CUDA(cudaMalloc(&net->d_rows_tmp, need));
-        net->rows_tmp_bytes = need;
+    if (d.row1 - d.row0 < STRIP_HALO) {
+        // the halo would reach into the strip after next, which this protocol does not exchange
+        set_error("qv_strip_attach: the neighbour holds %d rows, fewer than the %d-row halo (use fewer strips)", d.row1 - d.row0, STRIP_HALO);
+        return QV_ERR_ARG;
     }
-    rc = run_forward(net, d_in, net->d_rows_tmp, 1, in_rows, net->W, st);
+    int rc = set_device(net);
     if (rc) return rc;
-    QV_CUDA(cudaMemcpyAsync(d_out, net->d_rows_tmp + (size_t)(out_row0 - in_row0) * W, (size_t)(out_row1 - out_row0) * W,
-                            cudaMemcpyDeviceToDevice, st));
-    if (!cuda_stream) QV_CUDA(cudaStreamSynchronize(st));
+    StripPeer &P = S.peer[side];
+    if (P.attached && P.ipc && P.base) cudaIpcCloseMemHandle(P.base);
+    P = StripPeer{};
+    if (d.nonce == process_nonce()) {
+        // same process: plain peer access to the neighbour's allocation
+        if (d.dev != net->dev) {
+            int can = 0;
+            QV_CUDA(cudaDeviceCanAccessPeer(&can, net->dev, d.dev));
+            if (!can) { set_error("qv_strip_attach: device %d cannot map memory of device %d (no peer access)", net->dev, d.dev); return QV_ERR_CUDA; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(d.dev, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            QV_CUDA(e);
+        }
+        P.base = (uint8_t *)(uintptr_t)d.base;
+    } else {
+        void *p = nullptr;
+        QV_CUDA(cudaIpcOpenMemHandle(&p, d.ipc, cudaIpcMemLazyEnablePeerAccess));
+        P.base = (uint8_t *)p;
+        P.ipc = true;
+    }
+    P.d = d;
+    char my_pci[16] = {0};
+    QV_CUDA(cudaDeviceGetPCIBusId(my_pci, (int)sizeof(my_pci), net->dev));
+    P.same_device = strncmp(my_pci, d.pci, sizeof(my_pci)) == 0;
+    P.attached = true;
+    return QV_OK;
+}
+
+int qv_strip_input(qv_net *net, int slot, void **d_rows)
+{
+    if (!net || !d_rows || slot < 0 || slot > 1) { set_error("qv_strip_input: bad argument"); return QV_ERR_ARG; }
+    if (!net->strip.on) { set_error("qv_strip_input: qv_strip_setup has not been called"); return QV_ERR_STATE; }
+    *d_rows = net->strip.block + STRIP_HDR + (size_t)slot * net->strip.slot_stride;
+    return QV_OK;
+}
+
+int qv_strip_acquire(qv_net *net, int slot, void *cuda_stream)
+{
+    if (!net || slot < 0 || slot > 1) { set_error("qv_strip_acquire: bad argument"); return QV_ERR_ARG; }
+    StripState &S = net->strip;
+    if (!S.on) { set_error("qv_strip_acquire: qv_strip_setup has not been called"); return QV_ERR_STATE; }
+    int rc = set_device(net);
+    if (rc) return rc;
+    const uint32_t s = S.slot_seq[slot];
+    if (s == 0 || !net->fm) return QV_OK;
+    // the neighbours read this slot's rows in their step s: wait until they have completed it
+    const uint32_t *a = S.peer[0].attached ? reinterpret_cast<const uint32_t *>(S.peer[0].base + STRIP_DONE) : nullptr;
+    const uint32_t *b = S.peer[1].attached ? reinterpret_cast<const uint32_t *>(S.peer[1].base + STRIP_DONE) : nullptr;
+    QV_CUDA(fused_wait_words(net->fm, a, s, b, s, cuda_stream ? (cudaStream_t)cuda_stream : net->st));
+    net->launches += (a || b) ? 1 : 0;
+    return QV_OK;
+}
+
+int qv_strip_load(qv_net *net, int slot, const uint8_t *host_rows, void *cuda_stream)
+{
+    if (!host_rows) { set_error("qv_strip_load: null argument"); return QV_ERR_ARG; }
+    int rc = qv_strip_acquire(net, slot, cuda_stream);
+    if (rc) return rc;
+    StripState &S = net->strip;
+    QV_CUDA(cudaMemcpyAsync(S.block + STRIP_HDR + (size_t)slot * S.slot_stride, host_rows, (size_t)(S.row1 - S.row0) * net->W,
+                            cudaMemcpyHostToDevice, cuda_stream ? (cudaStream_t)cuda_stream : net->st));
+    return QV_OK;
+}
+
+int qv_strip_forward(qv_net *net, int slot, uint8_t *d_out, void *cuda_stream)
+{
+    if (!net || !d_out || slot < 0 || slot > 1) { set_error("qv_strip_forward: bad argument"); return QV_ERR_ARG; }
+    StripState &S = net->strip;
+    if (!S.on) { set_error("qv_strip_forward: qv_strip_setup has not been called"); return QV_ERR_STATE; }
+    if (!net->uploaded || !net->fm || net->impl == QV_IMPL_LAYERED) {
+        set_error("qv_strip_forward: needs a loaded model and the fused path (peer-mapped halo rows are read by the fused kernel)");
+        return QV_ERR_STATE;
+    }
+    if ((S.row0 > 0 && !S.peer[QV_STRIP_ABOVE].attached) || (S.row1 < S.img_h && !S.peer[QV_STRIP_BELOW].attached)) {
+        set_error("qv_strip_forward: rows [%d, %d) of %d have an interior edge with no neighbour attached", S.row0, S.row1, S.img_h);
+        return QV_ERR_STATE;
+    }
+    int rc = set_device(net);
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : net->st;
+    const size_t W = net->W;
+    const uint32_t seq = ++S.seq;
+    S.slot_seq[slot] = seq;
+    FusedRows fr;
+    fr.own0 = fr.out0 = S.row0; fr.own1 = fr.out1 = S.row1; fr.seq = seq;
+    fr.pub = reinterpret_cast<uint32_t *>(S.block + STRIP_PUB);
+    fr.done = reinterpret_cast<uint32_t *>(S.block + STRIP_DONE);
+    fr.done_ctr = reinterpret_cast<uint32_t *>(S.block + STRIP_CTR);
+    bool same_device_peer = false;
+    if (S.row0 > 0) {
+        const StripPeer &P = S.peer[QV_STRIP_ABOVE];
+        fr.top_rows = STRIP_HALO;
+        fr.d_top = P.base + P.d.slot_off + (size_t)slot * P.d.slot_stride + (size_t)(P.d.row1 - P.d.row0 - STRIP_HALO) * W;
+        fr.flag_top = reinterpret_cast<const uint32_t *>(P.base + STRIP_PUB);
+        same_device_peer |= P.same_device;
+    }
+    if (S.row1 < S.img_h) {
+        const StripPeer &P = S.peer[QV_STRIP_BELOW];
+        fr.bot_rows = STRIP_HALO;
+        fr.d_bot = P.base + P.d.slot_off + (size_t)slot * P.d.slot_stride;
+        fr.flag_bot = reinterpret_cast<const uint32_t *>(P.base + STRIP_PUB);
+        same_device_peer |= P.same_device;
+    }
+    // Normally the fused kernel publishes this GPU's rows when it starts and its input stage waits for the neighbours'.
+    // With several strips on one device (a neighbour, or just another strip of this process) a kernel that spins on
+    // every SM could keep the kernel it waits for from ever being scheduled: publish and wait on the stream instead,
+    // with one-warp kernels, and launch the fused kernel only once the rows are there.
+    const bool stream_level = same_device_peer || (net->dev < 64 && g_strip_handles[net->dev].load() > 1);
+    if (stream_level) {
+        QV_CUDA(fused_publish(fr.pub, seq, st));
+        QV_CUDA(fused_wait_words(net->fm, fr.flag_top, seq, fr.flag_bot, seq, st));
+        net->launches += (fr.flag_top || fr.flag_bot) ? 2 : 1;
+        fr.flag_top = fr.flag_bot = nullptr;
+    }
+    const uint8_t *own = S.block + STRIP_HDR + (size_t)slot * S.slot_stride;
+    QV_CUDA(fused_forward(net->fm, own, d_out, 1, S.img_h, net->W, st, &net->launches, &fr));
+    if (!cuda_stream) { QV_CUDA(cudaStreamSynchronize(st)); return kernel_report(net); }
     return QV_OK;
 }
 

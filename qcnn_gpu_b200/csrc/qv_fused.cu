@@ -55,6 +55,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -124,10 +125,22 @@ struct GroupQ {
 };
 
 struct FusedParams {
+    // Row r of frame f is read at in + f*frame_stride + r*W and written at out + f*frame_stride + r*W: `in` / `out` are
+    // VIRTUAL bases (buffer pointer minus first-row offset) when the buffers hold only a row window of the image.
     const uint8_t *in;
     uint8_t *out;
     const uint8_t *wimg;
     int n_frames, H, W, nstrips, nseg, seg_rows, n_units;
+    // Spatial partition of one frame over several GPUs (qv_strip_*): this launch produces image rows [ys, ye); `in` holds
+    // rows [own0, own1); rows [rlo, own0) are read through in_top and rows [own1, rhi) through in_bot -- virtual bases too,
+    // pointing into the NEIGHBOUR GPUs' memory (peer-mapped over NVLink), valid once *flag_top / *flag_bot have reached
+    // `seq`.  A whole-frame launch has ys = own0 = rlo = 0, ye = own1 = rhi = H and no flags.
+    int ys, ye, own0, own1, rlo, rhi;
+    size_t frame_stride;
+    const uint8_t *in_top, *in_bot;
+    const uint32_t *flag_top, *flag_bot;   // the neighbours' "rows published" words
+    uint32_t *pub, *done, *done_ctr;       // this GPU's own words: published sequence number, completed sequence number
+    uint32_t seq;
     GroupQ q1, q22, q21, q31, q32;
     int c4_bias, c4_mul, c4_shift;
     int c4_w[108];                     // C4 weights [tap][plane][4 words], 4 channels per word (CUDA-core dp4a)
@@ -172,6 +185,20 @@ __device__ __forceinline__ void warp_wait(uint64_t *bar, uint32_t parity, int la
 {
     if (lane == 0 && !tc::mbar_wait(bar, parity)) *fail = 1;
     __syncwarp();
+}
+
+// Strip mode: spin (bounded, ~2 s) until a neighbour GPU's "rows published" word has reached `seq`.  The acquire at system
+// scope orders the halo-row loads that follow behind the neighbour's release (k_fused publishes at its start: the rows
+// were complete before the launch by stream order).
+__device__ __forceinline__ bool peer_wait(const uint32_t *flag, uint32_t seq)
+{
+    for (int n = 0; n < 4000000; ++n) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - seq) >= 0) return true;
+        __nanosleep(200);
+    }
+    return false;
 }
 
 // workers / C4 warps -> MMA warp, event ev: every lane arrives on named barrier 2 + ev mod 3, the MMA warp blocks in
@@ -252,6 +279,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = P.H, W = P.W;
 
+    // strip mode: this GPU's rows were complete before the launch (stream order) -- tell the neighbours
+    if (P.pub && blockIdx.x == 0 && tid == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.pub), "r"(P.seq) : "memory");
     // ---- one-time setup: weights -> smem, barriers, TMEM ---------------------------------
     for (int i = tid; i < WIMG_BYTES / 16; i += NTHREADS)
         reinterpret_cast<uint4 *>(sm)[i] = reinterpret_cast<const uint4 *>(P.wimg)[i];
@@ -288,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         const uint32_t r22 = tm + TM_R22, r21 = tm + TM_R21, r31 = tm + TM_R31;
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg;
-            const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
+            const int y0 = P.ys + seg * P.seg_rows, y1 = min(P.ye, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             int ph = mod_pos(y0 - 4, N_PHASE);
             for (int i = 0; i < niter; ++i) {
@@ -372,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
             const int X0 = strip * WT;
-            const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
+            const int y0 = P.ys + seg * P.seg_rows, y1 = min(P.ye, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             // ---- prologue: the previous unit's accumulators are drained (nothing of this unit is in flight yet) ------------
             worker_bar();
@@ -472,17 +501,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
             const int X0 = strip * WT;
-            const int y0 = seg * P.seg_rows, y1 = min(H, y0 + P.seg_rows);
+            const int y0 = P.ys + seg * P.seg_rows, y1 = min(P.ye, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
-            const uint8_t *inf = P.in + (size_t)f * H * W;
-            uint8_t *outf = P.out + (size_t)f * H * W;
+            const uint8_t *inf = P.in + (size_t)f * P.frame_stride;
+            uint8_t *outf = P.out + (size_t)f * P.frame_stride;
             const bool col_ok = mo < WT && X0 + mo < W;
             // The input ring: 136 bytes (image columns X0-8 ..) of 32 rows; thread mo loads byte mo, threads 0-7 also byte 128 + mo.
             const int col_a = X0 - 8 + mo, col_b = col_a + 128;
             const bool ok_a = col_a >= 0 && col_a < W, ok_b = mo < PW - 128 && col_b < W;
             auto load_in = [&](int row) -> unsigned {
-                const bool rok = row >= 0 && row < H;
-                const uint8_t *rp = inf + (size_t)row * W;
+                const bool rok = row >= P.rlo && row < P.rhi;
+                const uint8_t *rp = (row < P.own0 ? P.in_top : (row >= P.own1 ? P.in_bot : inf)) + (ptrdiff_t)row * W;
                 const unsigned a = (rok && ok_a) ? (unsigned)rp[col_a] : 128u;
                 const unsigned b = (rok && ok_b) ? (unsigned)rp[col_b] : 128u;
                 return a | (b << 8);
@@ -512,6 +541,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             };
             int c3 = mod_pos(y0 - 4, 3);
             int c4_s1 = 0, c4_s2 = 0;
+            // ---- rows of a neighbour GPU: wait until it has published them (one lane per warp polls over NVLink) ----
+            if (P.flag_top && y0 - 6 < P.own0 && P.rlo < P.own0) { if (lane == 0 && !peer_wait(P.flag_top, P.seq)) *s_fail = 3; __syncwarp(); }
+            if (P.flag_bot && y1 + PIPE > P.own1 && P.rhi > P.own1) { if (lane == 0 && !peer_wait(P.flag_bot, P.seq)) *s_fail = 3; __syncwarp(); }
             // ---- prologue: input rows for a1 rows y0-4 and y0-3, C1 operand of the first ------------
             for (int r = y0 - 6; r <= y0 - 1; ++r) store_in(r, load_in(r));
             worker_bar();
@@ -565,9 +597,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         *reinterpret_cast<volatile int *>(P.fail_flag) = *s_fail;
         __threadfence_system();
     }
-    if (tid == 0 && *s_fail)
+    // strip mode: the last CTA to finish tells the neighbours that this GPU no longer reads their rows of step `seq`
+    if (P.done && tid == 0) {
+        __threadfence();
+        if (atomicAdd(P.done_ctr, 1u) == gridDim.x - 1) {
+            *P.done_ctr = 0;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.done), "r"(P.seq) : "memory");
+        }
+    }
+    if (tid == 0 && *s_fail == 3) printf("qv fused kernel: block %d waited in vain for a neighbour GPU's rows (step %u)\n", blockIdx.x, P.seq);
+    else if (tid == 0 && *s_fail)
         printf(*s_fail == 2 ? "qv fused kernel: block %d has other shared-memory / TMEM bases than the descriptor table was built for\n"
                             : "qv fused kernel: mbarrier wait timed out in block %d\n", blockIdx.x);
+}
+
+// ---- strip protocol helpers (stream-ordered, one thread each) -----------------------------------------------------
+__global__ void k_publish(uint32_t *word, uint32_t value)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(word), "r"(value) : "memory");
+}
+__global__ void k_wait_words(const uint32_t *a, uint32_t va, const uint32_t *b, uint32_t vb, int *fail_flag)
+{
+    const uint32_t *w = threadIdx.x == 0 ? a : b;
+    const uint32_t v = threadIdx.x == 0 ? va : vb;
+    if (w && !peer_wait(w, v)) { *reinterpret_cast<volatile int *>(fail_flag) = 3; __threadfence_system(); }
 }
 
 // Shared-memory window base and TMEM base a CTA of k_fused sees (same launch shape: dynamic smem only, all 512 columns).
@@ -655,7 +708,17 @@ struct FusedModel {
     FusedParams proto{};
     bool fast = true;
     int sm_count = 148;
+    // environment switches, read once at upload (never on the per-launch path)
+    bool env_profile = false, env_test_fail = false;
+    int env_experiment = 0;
 };
+
+// The operand table lives in constant memory: one copy per device, and its content depends only on the shared-memory
+// window / TMEM bases a CTA of this launch shape gets -- the same for every model.  It is written once per device, under
+// a lock, so that distinct handles can load models from distinct threads (include/qvrcnn_b200.h).
+static std::mutex g_ops_mu;
+struct OpsRecord { bool done = false; uint32_t sbase16 = 0, tmem_base = 0; };
+static OpsRecord g_ops_done[64];
 
 // Writes 16 K-bytes of row n, K-chunk j, of a B block laid out [2][NR][16].
 static void put_chunk(uint8_t *blk, int NR, int j, int n, const int8_t *src16) { memcpy(blk + ((size_t)j * NR + n) * 16, src16, 16); }
@@ -801,29 +864,35 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_bases, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) {
-        // descriptor table in constant memory, for the shared-memory / TMEM bases a CTA of this launch shape gets
-        uint32_t *d_b = nullptr, h_b[2] = {0, 0};
-        e = cudaMalloc(&d_b, 8);
-        if (e == cudaSuccess) {
-            k_bases<<<1, 32, SMEM_BYTES, st>>>(d_b);
-            e = cudaMemcpyAsync(h_b, d_b, 8, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            cudaFree(d_b);
-        }
-        if (e == cudaSuccess) {
-            PhaseBases pb[N_PHASE];
-            FixedBases fb;
-            build_mma_bases(h_b[0] >> 4, h_b[1], pb, fb);
-            P.sbase16 = h_b[0] >> 4; P.tmem_base = h_b[1];
-            static PhaseOps ops[N_PHASE];       // static: the async copy reads it until the synchronize below
-            build_mma_ops(pb, fb, ops);
-            e = cudaMemcpyToSymbolAsync(c_ops, ops, sizeof(ops), 0, cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        }
-    }
     int dev = 0, sms = 148;
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && (dev < 0 || dev >= 64)) e = cudaErrorInvalidDevice;
+    if (e == cudaSuccess) {
+        // descriptor table in constant memory, for the shared-memory / TMEM bases a CTA of this launch shape gets
+        std::lock_guard<std::mutex> lock(g_ops_mu);
+        OpsRecord &rec = g_ops_done[dev];
+        if (!rec.done) {
+            uint32_t *d_b = nullptr, h_b[2] = {0, 0};
+            e = cudaMalloc(&d_b, 8);
+            if (e == cudaSuccess) {
+                k_bases<<<1, 32, SMEM_BYTES, st>>>(d_b);
+                e = cudaMemcpyAsync(h_b, d_b, 8, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                cudaFree(d_b);
+            }
+            if (e == cudaSuccess) {
+                PhaseBases pb[N_PHASE];
+                FixedBases fb;
+                build_mma_bases(h_b[0] >> 4, h_b[1], pb, fb);
+                std::vector<PhaseOps> ops(N_PHASE);      // outlives the copy: synchronised below
+                build_mma_ops(pb, fb, ops.data());
+                e = cudaMemcpyToSymbolAsync(c_ops, ops.data(), sizeof(PhaseOps) * N_PHASE, 0, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e == cudaSuccess) { rec.done = true; rec.sbase16 = h_b[0] >> 4; rec.tmem_base = h_b[1]; }
+            }
+        }
+        P.sbase16 = rec.sbase16; P.tmem_base = rec.tmem_base;
+    }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) {
         set_error("fused_upload: %s", cudaGetErrorString(e));
@@ -832,6 +901,9 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
         return nullptr;
     }
     fm->sm_count = sms;
+    fm->env_profile = getenv("QV_FUSED_PROFILE") != nullptr;
+    fm->env_experiment = getenv("QV_FUSED_EXPERIMENT") ? atoi(getenv("QV_FUSED_EXPERIMENT")) : 0;
+    fm->env_test_fail = getenv("QV_FUSED_TEST_FAIL") != nullptr;     // tests only: make every CTA report a base mismatch
     P.wimg = fm->d_wimg;
     P.fail_flag = nullptr;
     if (cudaHostAlloc(&fm->h_fail, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
@@ -846,6 +918,19 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
         return nullptr;
     }
     return fm;
+}
+
+cudaError_t fused_publish(uint32_t *word, uint32_t value, cudaStream_t st)
+{
+    k_publish<<<1, 1, 0, st>>>(word, value);
+    return cudaGetLastError();
+}
+
+cudaError_t fused_wait_words(const FusedModel *fm, const uint32_t *a, uint32_t va, const uint32_t *b, uint32_t vb, cudaStream_t st)
+{
+    if (!a && !b) return cudaSuccess;
+    k_wait_words<<<1, 2, 0, st>>>(a, va, b, vb, fm->proto.fail_flag);
+    return cudaGetLastError();
 }
 
 void fused_free(FusedModel *fm)
@@ -865,11 +950,36 @@ int fused_take_failure(const FusedModel *fm)
 }
 
 cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_out, int n, int H, int W, cudaStream_t st,
-                          long long *launches)
+                          long long *launches, const FusedRows *rows)
 {
     if (n <= 0) return cudaSuccess;
     FusedParams P = fm->proto;
-    P.in = d_in; P.out = d_out; P.n_frames = n; P.H = H; P.W = W;
+    P.n_frames = n; P.H = H; P.W = W;
+    P.frame_stride = (size_t)H * W;
+    P.in = d_in; P.out = d_out;
+    P.ys = P.own0 = P.rlo = 0; P.ye = P.own1 = P.rhi = H;
+    P.in_top = P.in_bot = nullptr; P.flag_top = P.flag_bot = nullptr;
+    P.pub = P.done = P.done_ctr = nullptr; P.seq = 0;
+    if (rows) {
+        // one frame, a row window of it: H is the height of the IMAGE (each layer's zero padding applies at the image
+        // edges only, inference/cnn.cu:44-49), the buffers hold the rows the launch description names
+        if (n != 1 || rows->own0 < 0 || rows->own1 > H || rows->own0 >= rows->own1 || rows->out0 < rows->own0 || rows->out1 > rows->own1 ||
+            rows->out0 > rows->out1 || rows->top_rows < 0 || rows->bot_rows < 0)
+            return cudaErrorInvalidValue;
+        if (rows->out0 == rows->out1) return cudaSuccess;
+        P.own0 = rows->own0; P.own1 = rows->own1; P.ys = rows->out0; P.ye = rows->out1;
+        P.rlo = rows->d_top ? rows->own0 - rows->top_rows : rows->own0;
+        P.rhi = rows->d_bot ? rows->own1 + rows->bot_rows : rows->own1;
+        if (P.rlo < 0 || P.rhi > H) return cudaErrorInvalidValue;
+        P.in = d_in - (ptrdiff_t)rows->own0 * W;
+        P.out = d_out - (ptrdiff_t)rows->out0 * W;
+        P.in_top = rows->d_top ? rows->d_top - (ptrdiff_t)P.rlo * W : nullptr;
+        P.in_bot = rows->d_bot ? rows->d_bot - (ptrdiff_t)rows->own1 * W : nullptr;
+        P.flag_top = rows->d_top ? rows->flag_top : nullptr;
+        P.flag_bot = rows->d_bot ? rows->flag_bot : nullptr;
+        P.pub = rows->pub; P.done = rows->done; P.done_ctr = rows->done_ctr; P.seq = rows->seq;
+    }
+    const int rows_out = P.ye - P.ys;
     P.nstrips = (W + WT - 1) / WT;
     // Row segments.  Units are dealt to the persistent CTAs round-robin, so the makespan is
     // ceil(units / SMs) * (rows per segment + PIPE) row-iterations; pick the cut that minimises it
@@ -878,24 +988,24 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     int nseg = 1;
     {
         long long best = -1;
-        const int max_seg = std::max(1, std::min(H / 16, 256));
+        const int max_seg = std::max(1, std::min(rows_out / 16, 256));
         for (int c = 1; c <= max_seg; ++c) {
-            const int rows = (H + c - 1) / c, real = (H + rows - 1) / rows;
+            const int rws = (rows_out + c - 1) / c, real = (rows_out + rws - 1) / rws;
             const long long waves = (cols * real + fm->sm_count - 1) / fm->sm_count;
-            const long long cost = waves * (rows + PIPE);
+            const long long cost = waves * (rws + PIPE);
             if (best < 0 || cost < best) { best = cost; nseg = c; }
         }
     }
-    P.seg_rows = (H + nseg - 1) / nseg;
-    P.nseg = (H + P.seg_rows - 1) / P.seg_rows;
+    P.seg_rows = (rows_out + nseg - 1) / nseg;
+    P.nseg = (rows_out + P.seg_rows - 1) / P.seg_rows;
     const long long units = cols * P.nseg;
     if (units > 0x7fffffffll) return cudaErrorInvalidValue;
     P.n_units = (int)units;
     const int grid = (int)std::min<long long>(units, fm->sm_count);
-    const bool prof = getenv("QV_FUSED_PROFILE") != nullptr;
+    const bool prof = fm->env_profile;
     P.dbg = nullptr;
-    P.dbg_flags = getenv("QV_FUSED_EXPERIMENT") ? atoi(getenv("QV_FUSED_EXPERIMENT")) : 0;
-    if (getenv("QV_FUSED_TEST_FAIL")) P.sbase16 ^= 1u;        // tests only: make every CTA report a base mismatch
+    P.dbg_flags = fm->env_experiment;
+    if (fm->env_test_fail) P.sbase16 ^= 1u;
     const size_t dbg_n = (size_t)grid * 16 + TR_N * 48;
     if (prof && cudaMalloc(&P.dbg, dbg_n * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
     if (P.dbg) cudaMemsetAsync(P.dbg, 0, dbg_n * sizeof(long long), st);

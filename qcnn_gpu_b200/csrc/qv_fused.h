@@ -13,11 +13,27 @@ struct FusedModel;   // device-resident weights / descriptors in the layout the 
 // Builds the device image of the model for the fused kernel. Returns nullptr + error on failure.
 FusedModel *fused_upload(const ModelHost &m, cudaStream_t st);
 void fused_free(FusedModel *fm);
-// Whole net on n frames of HxW luma resident in device memory, one launch.
+// A row window of ONE frame (spatial partition over several GPUs): the launch produces image rows [out0, out1) into d_out
+// (first row = out0) from d_in, which holds image rows [own0, own1); up to 6 rows above / below come from d_top (first row
+// = own0 - top_rows) and d_bot (first row = own1) -- typically the neighbour GPUs' memory, peer-mapped -- once the
+// neighbours' publish words have reached `seq`.  pub / done / done_ctr are this GPU's own words (any may be null).
+struct FusedRows {
+    int own0 = 0, own1 = 0, out0 = 0, out1 = 0, top_rows = 0, bot_rows = 0;
+    const uint8_t *d_top = nullptr, *d_bot = nullptr;
+    const uint32_t *flag_top = nullptr, *flag_bot = nullptr;
+    uint32_t *pub = nullptr, *done = nullptr, *done_ctr = nullptr;
+    uint32_t seq = 0;
+};
+// Whole net on n frames of HxW luma resident in device memory, one launch.  With `rows`: n = 1, H = image height.
 cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_out, int n, int H, int W,
-                          cudaStream_t st, long long *launches);
+                          cudaStream_t st, long long *launches, const FusedRows *rows = nullptr);
+// Tiny stream-ordered helpers of the strip protocol: set *word = value with system-scope release; spin (bounded) until
+// *a >= va and *b >= vb (either pointer may be null), reporting a timeout through the model's failure word (code 3).
+cudaError_t fused_publish(uint32_t *word, uint32_t value, cudaStream_t st);
+cudaError_t fused_wait_words(const FusedModel *fm, const uint32_t *a, uint32_t va, const uint32_t *b, uint32_t vb, cudaStream_t st);
 // After the stream the kernel ran on has been synchronised: 0, or what a CTA reported (1 = an mbarrier wait timed
-// out, 2 = shared-memory / TMEM bases other than the operand table was built for); the report is cleared.
+// out, 2 = shared-memory / TMEM bases other than the operand table was built for, 3 = a neighbour GPU's rows never
+// arrived); the report is cleared.
 int fused_take_failure(const FusedModel *fm);
 
 // Test hook (no GPU): weight image, per-phase MMA operand table (bases 0) and constants as the host builds them.

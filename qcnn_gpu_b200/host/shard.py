@@ -7,8 +7,10 @@ The reference is single-GPU (device 0 hard-wired, inference/kernel.cu:86); the p
   * inside one frame the net is a stencil of radius 2+2+1+1 = 6 rows: horizontal strips with a 6-row
     INPUT halo from each neighbour (one neighbour exchange before compute), outputs disjoint.
 The only collective is the sum of the exact int64 SSE for the PSNR report (inference/yuv_data.cpp:87-97).
-Everything here is backend-agnostic (NCCL on GPUs, gloo in the CPU tests): the per-rank compute is a
-callable supplied by the caller.
+Everything here is backend-agnostic: the per-rank compute is a callable supplied by the caller.  On GPUs the
+halo rows are NOT exchanged by this module: the fused kernel reads them from the neighbours' peer-mapped
+memory (qv_strip_*, host/multi_gpu.py); exchange_halos is the message-passing statement of the same
+partition, used by the gloo CPU tests and by callers without peer access.
 """
 from __future__ import annotations
 
@@ -24,7 +26,11 @@ def split(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def strip_window(h: int, rank: int, world: int) -> Tuple[int, int, int, int]:
-    """(y0, y1, r0, r1): rank's output rows [y0,y1) and the input rows [r0,r1) it needs (6-row halo, clipped)."""
+    """(y0, y1, r0, r1): rank's output rows [y0,y1) and the input rows [r0,r1) it needs (6-row halo, clipped).
+    Every strip must hold at least HALO rows: the halo of a strip then lies entirely inside its direct neighbours
+    (a shorter strip would need rows of the strip after next, which neither exchange_halos nor qv_strip_* carry)."""
+    if world > 1 and h // world < HALO:
+        raise ValueError("%d rows over %d ranks leaves strips shorter than the %d-row halo: use fewer ranks" % (h, world, HALO))
     y0, n = split(h, rank, world)
     y1 = y0 + n
     return y0, y1, max(0, y0 - HALO), min(h, y1 + HALO)

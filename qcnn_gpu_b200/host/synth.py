@@ -32,12 +32,12 @@ def hash5(seed, stream, a, b, c):
     return k
 
 
-def make_frames(seed: int, frames: int, h: int, w: int, first_frame: int = 0):
+def make_frames(seed: int, frames: int, h: int, w: int, first_frame: int = 0, rows=None):
     """Returns (anchor, ori) u8 [frames,h,w].  anchor = blocky 16x16 content + 5-bit noise
     (what an intra-coded frame looks like to the net); ori = anchor + small noise so that the
-    'before net' PSNR is finite."""
+    'before net' PSNR is finite.  rows = (y0, y1): only those rows of the h-row frames (a strip's share)."""
     f = (np.arange(frames, dtype=np.uint64) + np.uint64(first_frame))[:, None, None]
-    y = np.arange(h, dtype=np.uint64)[None, :, None]
+    y = (np.arange(h, dtype=np.uint64) if rows is None else np.arange(rows[0], rows[1], dtype=np.uint64))[None, :, None]
     x = np.arange(w, dtype=np.uint64)[None, None, :]
     base = (hash5(seed, 0, f, y >> np.uint64(4), x >> np.uint64(4)) & np.uint64(0xFF)).astype(np.int32)
     noise = (hash5(seed, 1, f, y, x) & np.uint64(0x1F)).astype(np.int32) - 16

@@ -48,8 +48,8 @@ def test_fused_kernel_uses_tcgen05_and_parks_its_waiters(sass):
         assert "NANOSLEEP" in text, name                                # mbarrier waits with a suspend-time hint
         assert "BAR.ARV" in text, name                                  # workers -> MMA warp through a named barrier
         if "ILb1ELb1E" not in name:                                     # (the profiling build keeps its counters in an array)
-            # no register spills: nothing is ever loaded back from local memory; the only store is printf's argument
-            assert not re.search(r"\bLDL\b", text) and len(re.findall(r"\bSTL\b", text)) <= 1, name
+            # no register spills: nothing is ever loaded back from local memory; the only stores are the arguments of the two failure printfs
+            assert not re.search(r"\bLDL\b", text) and len(re.findall(r"\bSTL\b", text)) <= 3, name
     # the issue loop of the product kernel forms no descriptor with vector-ALU work: between the first and the last
     # MMA there are only uniform-datapath instructions
     prod = next(v for k, v in fused.items() if "ILb1ELb0E" in k)

@@ -56,6 +56,17 @@ def _run(world, mode, tmp_path):
     return [np.load(os.path.join(tmp_path, "r%d.npz" % r)) for r in range(world)]
 
 
+def test_strips_shorter_than_the_halo_are_refused():
+    """A strip must hold at least the 6 halo rows its neighbours read: otherwise the halo would reach into the strip
+    after next, which no exchange carries (silent size mismatch / hang before)."""
+    assert shard.strip_window(47, 1, 7) == (7, 14, 1, 20)          # 47 // 7 = 6 rows: just enough
+    with pytest.raises(ValueError, match="shorter than the 6-row halo"):
+        shard.strip_window(47, 0, 8)                               # 47 // 8 = 5 rows
+    with pytest.raises(ValueError, match="shorter than the 6-row halo"):
+        shard.strip_window(5, 0, 2)
+    assert shard.strip_window(5, 0, 1) == (0, 5, 0, 5)             # a single rank has no neighbours
+
+
 def test_split_covers_everything():
     for n in (0, 1, 5, 64, 240):
         for world in (1, 2, 3, 8):

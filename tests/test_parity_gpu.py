@@ -227,7 +227,7 @@ def test_device_entry_and_sse(models):
     d_ori = torch.from_numpy(ori).cuda()
     d_out = torch.empty_like(d_in)
     acc = torch.zeros(1, dtype=torch.int64, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    st = api.stream_arg(torch.cuda.current_stream().cuda_stream)     # torch's legacy default stream, named explicitly
     net.forward_frames_device(d_in.data_ptr(), d_out.data_ptr(), 3, st)
     api.sse_device(d_out.data_ptr(), d_ori.data_ptr(), d_in.numel(), acc.data_ptr(), st)
     torch.cuda.synchronize()
@@ -264,16 +264,29 @@ def test_error_behaviour(models, tmp_path):
 
 def test_kernel_failure_is_reported(models, monkeypatch):
     """A CTA of the fused kernel that detects a problem (here: forced, the operand-table check) must surface as an
-    error code of the call that synchronises -- never as a silently wrong frame."""
+    error code of the call that synchronises -- never as a silently wrong frame.  (The switch is read when the model
+    is uploaded, not on the launch path.)"""
+    image = formats.write_model_vect_c(models[32])
     net = _net(models[32], 1, 64, 250, api.IMPL_LAYERED)
     _fused_or_skip(net, api.IMPL_FUSED)
     net.set_impl(api.IMPL_FUSED)
     x = np.full((1, 64, 250), 77, np.uint8)
     net.load_data(x)
     monkeypatch.setenv("QV_FUSED_TEST_FAIL", "1")
+    net.load_static_para_mem(image)
     with pytest.raises(api.QVError, match="operand table"):
         net.forward_blu()
+    # the asynchronous entry point cannot report it; qv_synchronize on the caller's stream does
+    import torch
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.empty_like(d_in)
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    net.forward_frames_device(d_in.data_ptr(), d_out.data_ptr(), 1, st.cuda_stream)
+    with pytest.raises(api.QVError, match="operand table"):
+        net.synchronize(st.cuda_stream)
     monkeypatch.delenv("QV_FUSED_TEST_FAIL")
+    net.load_static_para_mem(image)
     net.forward_blu()                                   # the report was consumed; the handle keeps working
     assert np.array_equal(net.get_recon(), _oracle(models[32]).forward_blu(x))
 
