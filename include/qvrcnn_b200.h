@@ -145,6 +145,10 @@ QV_API int qv_synchronize(qv_net *net, void *cuda_stream);
    from the neighbour's HBM.  Ordering is by sequence numbers in the same block, written and polled by the kernels
    themselves (system-scope release / acquire): no collective, no host synchronisation between frames.  All handles of a
    frame must make the same sequence of qv_strip_forward calls.  Fused path only.
+   One strip per GPU is the layout this is for.  Kernels of different launches must never wait for each other on ONE GPU
+   (nothing guarantees that they run at the same time), so strips that share a GPU -- a test layout -- are ordered by
+   stream order instead: the caller drives all of them on one stream, all loads of a frame before its forwards (a different
+   stream is refused), and strips of different PROCESSES on one GPU are refused by qv_strip_attach.
 
      each GPU:  qv_create(gpu, 1, 1, rows, W) ; load model ; qv_strip_setup(net, H, row0, row1) ; qv_strip_export(net, &d)
      exchange the 192-byte descriptors once (threads: a shared array; processes: any byte transport)

@@ -8,7 +8,7 @@
 //   --gpus <n>   frame-sharded over n devices, one host thread per device (no communication;
 //                the exact int64 SSE partial sums are added on the host)
 //   --save-recon <file>
-//   --strips <n> every frame is cut into n horizontal strips, strip i on device i mod <gpus> (one host thread per strip): the
+//   --strips <n> every frame is cut into n horizontal strips, strip i on device i mod <gpus> (one host thread per device): the
 //                single-very-large-frame partition.  Each GPU uploads only its own rows; the 6 halo rows either side are
 //                read by the kernel from the neighbour GPU's memory over NVLink (qv_strip_*), no host synchronisation
 //                and no collective between frames
@@ -76,42 +76,59 @@ static void testqvrcnn_strips(const char *ori_fn, const char *input_fn, const ch
         if (i > 0 && qv_strip_attach(nets[i], QV_STRIP_ABOVE, &desc[i - 1])) die("qv_strip_attach");
         if (i + 1 < S && qv_strip_attach(nets[i], QV_STRIP_BELOW, &desc[i + 1])) die("qv_strip_attach");
     }
-    std::vector<std::string> errs(S);
+    // One host thread per DEVICE.  A device with a single strip (the layout this mode is for) runs a two-slot pipeline on two
+    // streams: the upload of frame k+1 overlaps the compute of frame k, the forwards stay in frame order.  A device that
+    // hosts several strips (more strips than GPUs: a test layout) drives all of them on ONE stream, frame by frame, all
+    // loads before the forwards: strips on one GPU are ordered by stream order, never by kernels waiting for each other.
+    std::vector<std::string> errs(G);
     auto t0 = std::chrono::steady_clock::now();
     {
         std::vector<std::thread> th;
-        for (int i = 0; i < S; ++i)
-            th.emplace_back([&, i] {
-                // two slots: the upload of frame k+1 overlaps the compute of frame k; the forwards stay in frame order
-                const size_t bytes = (size_t)(r1[i] - r0[i]) * W;
+        for (int g = 0; g < G; ++g)
+            th.emplace_back([&, g] {
+                std::vector<int> mine;
+                for (int i = g; i < S; i += G) mine.push_back(i);
+                if (mine.empty()) return;
+                const bool solo = mine.size() == 1;
                 cudaStream_t st[2] = {nullptr, nullptr};
                 cudaEvent_t ev = nullptr;
-                uint8_t *d_out[2] = {nullptr, nullptr};
-                bool ok = cudaSetDevice(i % G) == cudaSuccess && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
-                for (int s = 0; s < 2 && ok; ++s)
-                    ok = cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) == cudaSuccess && cudaMalloc(&d_out[s], bytes) == cudaSuccess;
-                if (!ok) errs[i] = "CUDA setup failed";
+                std::vector<uint8_t *> d_out(mine.size() * 2, nullptr);
+                bool ok = cudaSetDevice(g) == cudaSuccess && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+                for (int s = 0; s < 2 && ok; ++s) ok = cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) == cudaSuccess;
+                for (size_t j = 0; j < mine.size() && ok; ++j)
+                    for (int s = 0; s < 2 && ok; ++s)
+                        ok = cudaMalloc(&d_out[j * 2 + s], (size_t)(r1[mine[j]] - r0[mine[j]]) * W) == cudaSuccess;
+                if (!ok) errs[g] = "CUDA setup failed";
                 for (int k = 0; k < frame && ok; ++k) {
                     const int s = k & 1;
-                    const size_t off = (size_t)k * fpx + (size_t)r0[i] * W;
-                    ok = qv_strip_load(nets[i], s, test_data.input + off, st[s]) == QV_OK;
-                    if (ok && k > 0) ok = cudaStreamWaitEvent(st[s], ev, 0) == cudaSuccess;
-                    if (ok) ok = qv_strip_forward(nets[i], s, d_out[s], st[s]) == QV_OK;
-                    if (ok) ok = cudaEventRecord(ev, st[s]) == cudaSuccess;
-                    if (ok) ok = cudaMemcpyAsync(test_data.recon + off, d_out[s], bytes, cudaMemcpyDeviceToHost, st[s]) == cudaSuccess;
+                    cudaStream_t q = solo ? st[s] : st[0];
+                    for (size_t j = 0; j < mine.size() && ok; ++j)
+                        ok = qv_strip_load(nets[mine[j]], s, test_data.input + (size_t)k * fpx + (size_t)r0[mine[j]] * W, q) == QV_OK;
+                    if (ok && solo && k > 0) ok = cudaStreamWaitEvent(q, ev, 0) == cudaSuccess;
+                    for (size_t j = 0; j < mine.size() && ok; ++j)
+                        ok = qv_strip_forward(nets[mine[j]], s, d_out[j * 2 + s], q) == QV_OK;
+                    if (ok && solo) ok = cudaEventRecord(ev, q) == cudaSuccess;
+                    for (size_t j = 0; j < mine.size() && ok; ++j) {
+                        const int i = mine[j];
+                        ok = cudaMemcpyAsync(test_data.recon + (size_t)k * fpx + (size_t)r0[i] * W, d_out[j * 2 + s], (size_t)(r1[i] - r0[i]) * W,
+                                             cudaMemcpyDeviceToHost, q) == cudaSuccess;
+                    }
                 }
+                if (!ok && errs[g].empty()) errs[g] = qv_last_error();      // thread-local: copy it here
                 for (int s = 0; s < 2; ++s)
-                    if (st[s] && qv_synchronize(nets[i], st[s]) != QV_OK) ok = false;
-                if (!ok && errs[i].empty()) errs[i] = qv_last_error();      // thread-local: copy it here
-                for (int s = 0; s < 2; ++s) { cudaFree(d_out[s]); if (st[s]) cudaStreamDestroy(st[s]); }
+                    if (st[s] && qv_synchronize(nets[mine[0]], st[s]) != QV_OK && errs[g].empty()) errs[g] = qv_last_error();
+                for (size_t j = 1; j < mine.size(); ++j)
+                    if (qv_synchronize(nets[mine[j]], st[0]) != QV_OK && errs[g].empty()) errs[g] = qv_last_error();
+                for (uint8_t *p : d_out) cudaFree(p);
+                for (int s = 0; s < 2; ++s) if (st[s]) cudaStreamDestroy(st[s]);
                 if (ev) cudaEventDestroy(ev);
             });
         for (auto &t : th) t.join();
     }
     auto t1 = std::chrono::steady_clock::now();
     const long long us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
-    for (int i = 0; i < S; ++i)
-        if (!errs[i].empty()) { printf("strip %d: %s\n", i, errs[i].c_str()); exit(1); }
+    for (int g = 0; g < G; ++g)
+        if (!errs[g].empty()) { printf("GPU %d: %s\n", g, errs[g].c_str()); exit(1); }
     for (auto *n : nets) qv_destroy(n);
     if (!opt.save_recon.empty()) test_data.save_recon_as(opt.save_recon.c_str());
     const double psnr1 = test_data.psnr(test_data.input), psnr2 = test_data.psnr(test_data.recon);

@@ -45,6 +45,7 @@ struct StripDescImpl {                          // the content of qv_strip_desc
     int32_t dev, row0, row1, width, img_h;
     uint64_t nonce;                             // identifies the exporting process
     uint64_t base, slot_off, slot_stride;
+    uint64_t net;                               // the exporting handle (meaningful inside the exporting process only)
     cudaIpcMemHandle_t ipc;
     char pci[16];                               // PCI bus id of the device: device ordinals differ between processes
 };
@@ -52,6 +53,7 @@ static_assert(sizeof(StripDescImpl) <= sizeof(qv_strip_desc), "qv_strip_desc too
 struct StripPeer {
     bool attached = false, ipc = false, same_device = false;
     uint8_t *base = nullptr;
+    qv_net *net = nullptr;                      // same process only
     StripDescImpl d{};
 };
 struct StripState {
@@ -60,12 +62,16 @@ struct StripState {
     uint8_t *block = nullptr;
     size_t slot_stride = 0;
     uint32_t seq = 0, slot_seq[2] = {0, 0};
+    uint32_t fills[2] = {0, 0}, forwards[2] = {0, 0};   // per slot: how often acquired for filling / consumed (ordering checks between strips that share a GPU)
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
     StripPeer peer[2];                          // QV_STRIP_ABOVE, QV_STRIP_BELOW
 };
-// Strip-mode handles of this process per device.  A handle that is alone on its device lets the fused kernel itself wait
-// for the neighbours' rows; with several strips on one device a kernel spinning on every SM could keep the very kernel it
-// waits for from being scheduled, so those handles wait with a one-warp kernel on the stream instead.
-std::atomic<int> g_strip_handles[64];
+// Strip-mode handles of this process, per device.  Kernels that wait for one another must never share a GPU (nothing
+// guarantees that two launches on one GPU run at the same time), so strips that live on the SAME device are ordered by
+// the stream they are driven on instead: one stream for all of them, all loads of a frame before its forwards (checked).
+std::mutex g_strip_mu;
+std::vector<qv_net *> g_strip_nets[64];
 uint64_t process_nonce()
 {
     static const uint64_t n = [] {
@@ -508,7 +514,11 @@ int qv_strip_release(qv_net *net)
     strip_detach(net);
     cudaFree(net->strip.block);
     net->strip = StripState{};
-    if (net->dev >= 0 && net->dev < 64) g_strip_handles[net->dev].fetch_sub(1);
+    if (net->dev >= 0 && net->dev < 64) {
+        std::lock_guard<std::mutex> l(g_strip_mu);
+        auto &v = g_strip_nets[net->dev];
+        v.erase(std::remove(v.begin(), v.end(), net), v.end());
+    }
     return QV_OK;
 }
 
@@ -526,7 +536,10 @@ int qv_strip_setup(qv_net *net, int img_height, int row0, int row1)
     QV_CUDA(cudaMemset(S.block, 0, STRIP_HDR));
     QV_CUDA(cudaDeviceSynchronize());
     S.on = true;
-    if (net->dev >= 0 && net->dev < 64) g_strip_handles[net->dev].fetch_add(1);
+    if (net->dev >= 0 && net->dev < 64) {
+        std::lock_guard<std::mutex> l(g_strip_mu);
+        g_strip_nets[net->dev].push_back(net);
+    }
     return QV_OK;
 }
 
@@ -540,6 +553,7 @@ int qv_strip_export(qv_net *net, qv_strip_desc *out)
     d.magic = STRIP_MAGIC; d.dev = net->dev; d.row0 = net->strip.row0; d.row1 = net->strip.row1; d.width = net->W; d.img_h = net->strip.img_h;
     d.nonce = process_nonce();
     d.base = (uint64_t)(uintptr_t)net->strip.block; d.slot_off = STRIP_HDR; d.slot_stride = net->strip.slot_stride;
+    d.net = (uint64_t)(uintptr_t)net;
     QV_CUDA(cudaIpcGetMemHandle(&d.ipc, net->strip.block));
     QV_CUDA(cudaDeviceGetPCIBusId(d.pci, (int)sizeof(d.pci), net->dev));
     memset(out, 0, sizeof(*out));
@@ -581,7 +595,15 @@ int qv_strip_attach(qv_net *net, int side, const qv_strip_desc *neighbour)
             QV_CUDA(e);
         }
         P.base = (uint8_t *)(uintptr_t)d.base;
+        P.net = (qv_net *)(uintptr_t)d.net;
     } else {
+        char my_pci[16] = {0};
+        QV_CUDA(cudaDeviceGetPCIBusId(my_pci, (int)sizeof(my_pci), net->dev));
+        if (strncmp(my_pci, d.pci, sizeof(my_pci)) == 0) {
+            // two processes time-slicing one GPU: a kernel of one that waits for a kernel of the other may never see it run
+            set_error("qv_strip_attach: the neighbour strip belongs to another process on the SAME GPU; strips of different processes must be on different GPUs");
+            return QV_ERR_ARG;
+        }
         void *p = nullptr;
         QV_CUDA(cudaIpcOpenMemHandle(&p, d.ipc, cudaIpcMemLazyEnablePeerAccess));
         P.base = (uint8_t *)p;
@@ -603,6 +625,19 @@ int qv_strip_input(qv_net *net, int slot, void **d_rows)
     return QV_OK;
 }
 
+// Strips that share this handle's GPU (same process) are ordered by the one stream they must all be driven on.
+static int check_shared_device_stream(qv_net *net, cudaStream_t st, const char *who)
+{
+    std::lock_guard<std::mutex> l(g_strip_mu);
+    for (qv_net *o : g_strip_nets[net->dev])
+        if (o != net && o->strip.used && o->strip.last_stream != st) {
+            set_error("%s: several strips live on GPU %d: drive all of them on ONE caller-provided stream (kernels of different launches "
+                      "must not wait for each other on one GPU, so stream order is what orders them)", who, net->dev);
+            return QV_ERR_STATE;
+        }
+    return QV_OK;
+}
+
 int qv_strip_acquire(qv_net *net, int slot, void *cuda_stream)
 {
     if (!net || slot < 0 || slot > 1) { set_error("qv_strip_acquire: bad argument"); return QV_ERR_ARG; }
@@ -610,13 +645,29 @@ int qv_strip_acquire(qv_net *net, int slot, void *cuda_stream)
     if (!S.on) { set_error("qv_strip_acquire: qv_strip_setup has not been called"); return QV_ERR_STATE; }
     int rc = set_device(net);
     if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : net->st;
+    if ((rc = check_shared_device_stream(net, st, "qv_strip_acquire"))) return rc;
+    S.last_stream = st; S.used = true;
     const uint32_t s = S.slot_seq[slot];
-    if (s == 0 || !net->fm) return QV_OK;
-    // the neighbours read this slot's rows in their step s: wait until they have completed it
-    const uint32_t *a = S.peer[0].attached ? reinterpret_cast<const uint32_t *>(S.peer[0].base + STRIP_DONE) : nullptr;
-    const uint32_t *b = S.peer[1].attached ? reinterpret_cast<const uint32_t *>(S.peer[1].base + STRIP_DONE) : nullptr;
-    QV_CUDA(fused_wait_words(net->fm, a, s, b, s, cuda_stream ? (cudaStream_t)cuda_stream : net->st));
-    net->launches += (a || b) ? 1 : 0;
+    const uint32_t *w[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; ++side) {
+        const StripPeer &P = S.peer[side];
+        if (!P.attached || s == 0) continue;
+        if (P.same_device) {
+            // the neighbour's forward that read this slot must already be on the (shared) stream
+            if (P.net->strip.forwards[slot] < S.forwards[slot]) {
+                set_error("qv_strip_acquire: the neighbour strip on the same GPU has not yet consumed slot %d (issue the strips' calls frame by frame)", slot);
+                return QV_ERR_STATE;
+            }
+        } else {
+            w[side] = reinterpret_cast<const uint32_t *>(P.base + STRIP_DONE);      // another GPU: wait for its "completed step s"
+        }
+    }
+    if (net->fm && (w[0] || w[1])) {
+        QV_CUDA(fused_wait_words(net->fm, w[0], s, w[1], s, st));
+        net->launches += 1;
+    }
+    S.fills[slot] += 1;
     return QV_OK;
 }
 
@@ -647,40 +698,35 @@ int qv_strip_forward(qv_net *net, int slot, uint8_t *d_out, void *cuda_stream)
     int rc = set_device(net);
     if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : net->st;
+    if ((rc = check_shared_device_stream(net, st, "qv_strip_forward"))) return rc;
     const size_t W = net->W;
-    const uint32_t seq = ++S.seq;
-    S.slot_seq[slot] = seq;
     FusedRows fr;
-    fr.own0 = fr.out0 = S.row0; fr.own1 = fr.out1 = S.row1; fr.seq = seq;
+    fr.own0 = fr.out0 = S.row0; fr.own1 = fr.out1 = S.row1;
     fr.pub = reinterpret_cast<uint32_t *>(S.block + STRIP_PUB);
     fr.done = reinterpret_cast<uint32_t *>(S.block + STRIP_DONE);
     fr.done_ctr = reinterpret_cast<uint32_t *>(S.block + STRIP_CTR);
-    bool same_device_peer = false;
-    if (S.row0 > 0) {
-        const StripPeer &P = S.peer[QV_STRIP_ABOVE];
-        fr.top_rows = STRIP_HALO;
-        fr.d_top = P.base + P.d.slot_off + (size_t)slot * P.d.slot_stride + (size_t)(P.d.row1 - P.d.row0 - STRIP_HALO) * W;
-        fr.flag_top = reinterpret_cast<const uint32_t *>(P.base + STRIP_PUB);
-        same_device_peer |= P.same_device;
+    for (int side = 0; side < 2; ++side) {
+        if (side == QV_STRIP_ABOVE ? S.row0 == 0 : S.row1 == S.img_h) continue;
+        const StripPeer &P = S.peer[side];
+        const uint8_t *rows = P.base + P.d.slot_off + (size_t)slot * P.d.slot_stride;
+        const uint32_t *flag = reinterpret_cast<const uint32_t *>(P.base + STRIP_PUB);
+        if (P.same_device) {
+            // a neighbour on this very GPU: no kernel may wait for it -- its rows are ordered before this launch by the shared
+            // stream, provided its slot was filled for this frame already (checked here, on the host)
+            if (P.net->strip.fills[slot] == 0) {
+                set_error("qv_strip_forward: the neighbour strip on the same GPU has not filled slot %d yet (strips that share a GPU: all loads of a frame, then its forwards, on one stream)", slot);
+                return QV_ERR_STATE;
+            }
+            flag = nullptr;
+        }
+        if (side == QV_STRIP_ABOVE) { fr.top_rows = STRIP_HALO; fr.d_top = rows + (size_t)(P.d.row1 - P.d.row0 - STRIP_HALO) * W; fr.flag_top = flag; }
+        else { fr.bot_rows = STRIP_HALO; fr.d_bot = rows; fr.flag_bot = flag; }
     }
-    if (S.row1 < S.img_h) {
-        const StripPeer &P = S.peer[QV_STRIP_BELOW];
-        fr.bot_rows = STRIP_HALO;
-        fr.d_bot = P.base + P.d.slot_off + (size_t)slot * P.d.slot_stride;
-        fr.flag_bot = reinterpret_cast<const uint32_t *>(P.base + STRIP_PUB);
-        same_device_peer |= P.same_device;
-    }
-    // Normally the fused kernel publishes this GPU's rows when it starts and its input stage waits for the neighbours'.
-    // With several strips on one device (a neighbour, or just another strip of this process) a kernel that spins on
-    // every SM could keep the kernel it waits for from ever being scheduled: publish and wait on the stream instead,
-    // with one-warp kernels, and launch the fused kernel only once the rows are there.
-    const bool stream_level = same_device_peer || (net->dev < 64 && g_strip_handles[net->dev].load() > 1);
-    if (stream_level) {
-        QV_CUDA(fused_publish(fr.pub, seq, st));
-        QV_CUDA(fused_wait_words(net->fm, fr.flag_top, seq, fr.flag_bot, seq, st));
-        net->launches += (fr.flag_top || fr.flag_bot) ? 2 : 1;
-        fr.flag_top = fr.flag_bot = nullptr;
-    }
+    const uint32_t seq = ++S.seq;
+    S.slot_seq[slot] = seq;
+    S.forwards[slot] += 1;
+    S.last_stream = st; S.used = true;
+    fr.seq = seq;
     const uint8_t *own = S.block + STRIP_HDR + (size_t)slot * S.slot_stride;
     QV_CUDA(fused_forward(net->fm, own, d_out, 1, S.img_h, net->W, st, &net->launches, &fr));
     if (!cuda_stream) { QV_CUDA(cudaStreamSynchronize(st)); return kernel_report(net); }

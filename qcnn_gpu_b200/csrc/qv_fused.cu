@@ -266,7 +266,10 @@ __device__ __forceinline__ void c4_taps(const uint4 (&v)[3], const FusedParams &
         }
 }
 
-template <bool FAST, bool PROF>
+// ROWS: the launch covers a row window of one frame (strips over several GPUs).  The whole-frame instantiation keeps
+// the plain addressing: every instruction the C4 warps spend on the input ring is taken from the MMA warp's issue slots
+// (same SM sub-partition), and the window arithmetic cost 2.5 % at 64 x 1080p (profiles/r2_kernel_ab_rowwindow.log).
+template <bool FAST, bool PROF, bool ROWS>
 __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ FusedParams P)
 {
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     const int H = P.H, W = P.W;
 
     // strip mode: this GPU's rows were complete before the launch (stream order) -- tell the neighbours
-    if (P.pub && blockIdx.x == 0 && tid == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.pub), "r"(P.seq) : "memory");
+    if (ROWS && P.pub && blockIdx.x == 0 && tid == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.pub), "r"(P.seq) : "memory");
     // ---- one-time setup: weights -> smem, barriers, TMEM ---------------------------------
     for (int i = tid; i < WIMG_BYTES / 16; i += NTHREADS)
         reinterpret_cast<uint4 *>(sm)[i] = reinterpret_cast<const uint4 *>(P.wimg)[i];
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         const uint32_t r22 = tm + TM_R22, r21 = tm + TM_R21, r31 = tm + TM_R31;
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg;
-            const int y0 = P.ys + seg * P.seg_rows, y1 = min(P.ye, y0 + P.seg_rows);
+            const int y0 = (ROWS ? P.ys : 0) + seg * P.seg_rows, y1 = min(ROWS ? P.ye : H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             int ph = mod_pos(y0 - 4, N_PHASE);
             for (int i = 0; i < niter; ++i) {
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
             const int X0 = strip * WT;
-            const int y0 = P.ys + seg * P.seg_rows, y1 = min(P.ye, y0 + P.seg_rows);
+            const int y0 = (ROWS ? P.ys : 0) + seg * P.seg_rows, y1 = min(ROWS ? P.ye : H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             // ---- prologue: the previous unit's accumulators are drained (nothing of this unit is in flight yet) ------------
             worker_bar();
@@ -501,17 +504,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
             const int X0 = strip * WT;
-            const int y0 = P.ys + seg * P.seg_rows, y1 = min(P.ye, y0 + P.seg_rows);
+            const int y0 = (ROWS ? P.ys : 0) + seg * P.seg_rows, y1 = min(ROWS ? P.ye : H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
-            const uint8_t *inf = P.in + (size_t)f * P.frame_stride;
-            uint8_t *outf = P.out + (size_t)f * P.frame_stride;
+            const uint8_t *inf = P.in + (size_t)f * (ROWS ? P.frame_stride : (size_t)H * W);
+            uint8_t *outf = P.out + (size_t)f * (ROWS ? P.frame_stride : (size_t)H * W);
             const bool col_ok = mo < WT && X0 + mo < W;
             // The input ring: 136 bytes (image columns X0-8 ..) of 32 rows; thread mo loads byte mo, threads 0-7 also byte 128 + mo.
             const int col_a = X0 - 8 + mo, col_b = col_a + 128;
             const bool ok_a = col_a >= 0 && col_a < W, ok_b = mo < PW - 128 && col_b < W;
+            // does this unit read rows of a neighbour GPU at all?  (uniform; never in a whole-frame launch)
+            const bool peer_unit = ROWS && ((P.in_top && y0 - 6 < P.own0) || (P.in_bot && y1 + PIPE > P.own1));
             auto load_in = [&](int row) -> unsigned {
-                const bool rok = row >= P.rlo && row < P.rhi;
-                const uint8_t *rp = (row < P.own0 ? P.in_top : (row >= P.own1 ? P.in_bot : inf)) + (ptrdiff_t)row * W;
+                const bool rok = ROWS ? (unsigned)(row - P.rlo) < (unsigned)(P.rhi - P.rlo) : (row >= 0 && row < H);
+                const uint8_t *rp = inf + (size_t)row * W;
+                if (ROWS && peer_unit) rp = (row < P.own0 ? P.in_top : (row >= P.own1 ? P.in_bot : inf)) + (ptrdiff_t)row * W;
                 const unsigned a = (rok && ok_a) ? (unsigned)rp[col_a] : 128u;
                 const unsigned b = (rok && ok_b) ? (unsigned)rp[col_b] : 128u;
                 return a | (b << 8);
@@ -542,8 +548,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             int c3 = mod_pos(y0 - 4, 3);
             int c4_s1 = 0, c4_s2 = 0;
             // ---- rows of a neighbour GPU: wait until it has published them (one lane per warp polls over NVLink) ----
-            if (P.flag_top && y0 - 6 < P.own0 && P.rlo < P.own0) { if (lane == 0 && !peer_wait(P.flag_top, P.seq)) *s_fail = 3; __syncwarp(); }
-            if (P.flag_bot && y1 + PIPE > P.own1 && P.rhi > P.own1) { if (lane == 0 && !peer_wait(P.flag_bot, P.seq)) *s_fail = 3; __syncwarp(); }
+            if (ROWS && P.flag_top && y0 - 6 < P.own0 && P.rlo < P.own0) { if (lane == 0 && !peer_wait(P.flag_top, P.seq)) *s_fail = 3; __syncwarp(); }
+            if (ROWS && P.flag_bot && y1 + PIPE > P.own1 && P.rhi > P.own1) { if (lane == 0 && !peer_wait(P.flag_bot, P.seq)) *s_fail = 3; __syncwarp(); }
             // ---- prologue: input rows for a1 rows y0-4 and y0-3, C1 operand of the first ------------
             for (int r = y0 - 6; r <= y0 - 1; ++r) store_in(r, load_in(r));
             worker_bar();
@@ -598,7 +604,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         __threadfence_system();
     }
     // strip mode: the last CTA to finish tells the neighbours that this GPU no longer reads their rows of step `seq`
-    if (P.done && tid == 0) {
+    if (ROWS && P.done && tid == 0) {
         __threadfence();
         if (atomicAdd(P.done_ctr, 1u) == gridDim.x - 1) {
             *P.done_ctr = 0;
@@ -611,11 +617,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                             : "qv fused kernel: mbarrier wait timed out in block %d\n", blockIdx.x);
 }
 
-// ---- strip protocol helpers (stream-ordered, one thread each) -----------------------------------------------------
-__global__ void k_publish(uint32_t *word, uint32_t value)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(word), "r"(value) : "memory");
-}
+// ---- strip protocol helper (stream-ordered): wait for words that ANOTHER GPU writes -----------------------------------------------------
 __global__ void k_wait_words(const uint32_t *a, uint32_t va, const uint32_t *b, uint32_t vb, int *fail_flag)
 {
     const uint32_t *w = threadIdx.x == 0 ? a : b;
@@ -860,9 +862,11 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     cudaError_t e = cudaMalloc(&fm->d_wimg, WIMG_BYTES);
     if (e == cudaSuccess) e = cudaMemcpyAsync(fm->d_wimg, img.data(), WIMG_BYTES, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_bases, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     int dev = 0, sms = 148;
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
@@ -918,12 +922,6 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
         return nullptr;
     }
     return fm;
-}
-
-cudaError_t fused_publish(uint32_t *word, uint32_t value, cudaStream_t st)
-{
-    k_publish<<<1, 1, 0, st>>>(word, value);
-    return cudaGetLastError();
 }
 
 cudaError_t fused_wait_words(const FusedModel *fm, const uint32_t *a, uint32_t va, const uint32_t *b, uint32_t vb, cudaStream_t st)
@@ -1007,11 +1005,13 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     P.dbg_flags = fm->env_experiment;
     if (fm->env_test_fail) P.sbase16 ^= 1u;
     const size_t dbg_n = (size_t)grid * 16 + TR_N * 48;
-    if (prof && cudaMalloc(&P.dbg, dbg_n * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
+    if (prof && !rows && cudaMalloc(&P.dbg, dbg_n * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
     if (P.dbg) cudaMemsetAsync(P.dbg, 0, dbg_n * sizeof(long long), st);
-    if (fm->fast && P.dbg) k_fused<true, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
-    else if (fm->fast) k_fused<true, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
-    else k_fused<false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    if (rows && fm->fast) k_fused<true, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    else if (rows) k_fused<false, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    else if (fm->fast && P.dbg) k_fused<true, true, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    else if (fm->fast) k_fused<true, false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    else k_fused<false, false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     if (launches) *launches += 1;
     cudaError_t e = cudaGetLastError();
     if (P.dbg) {

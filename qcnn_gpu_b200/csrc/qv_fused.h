@@ -27,9 +27,8 @@ struct FusedRows {
 // Whole net on n frames of HxW luma resident in device memory, one launch.  With `rows`: n = 1, H = image height.
 cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_out, int n, int H, int W,
                           cudaStream_t st, long long *launches, const FusedRows *rows = nullptr);
-// Tiny stream-ordered helpers of the strip protocol: set *word = value with system-scope release; spin (bounded) until
-// *a >= va and *b >= vb (either pointer may be null), reporting a timeout through the model's failure word (code 3).
-cudaError_t fused_publish(uint32_t *word, uint32_t value, cudaStream_t st);
+// Stream-ordered helper of the strip protocol: spin (bounded) until *a >= va and *b >= vb (either pointer may be null; the
+// words live on OTHER GPUs), reporting a timeout through the model's failure word (code 3).
 cudaError_t fused_wait_words(const FusedModel *fm, const uint32_t *a, uint32_t va, const uint32_t *b, uint32_t vb, cudaStream_t st);
 // After the stream the kernel ran on has been synchronised: 0, or what a CTA reported (1 = an mbarrier wait timed
 // out, 2 = shared-memory / TMEM bases other than the operand table was built for, 3 = a neighbour GPU's rows never

@@ -73,11 +73,14 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int ma
     return false;
 }
 #else
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 20000)
+#ifndef QV_WAIT_HINT_NS
+#define QV_WAIT_HINT_NS 10000
+#endif
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 200000000 / QV_WAIT_HINT_NS)
 {
     if (mbar_try_wait(bar, parity)) return true;
     for (int n = 0; n < max_polls; ++n)
-        if (mbar_try_wait_hint(bar, parity, 10000u)) return true;
+        if (mbar_try_wait_hint(bar, parity, (uint32_t)QV_WAIT_HINT_NS)) return true;
     return false;
 }
 #endif

@@ -64,23 +64,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--uniq", type=int, default=4, help="distinct synthetic frames per rank (repeated)")
-    ap.add_argument("--one-gpu", action="store_true",
-                    help="tests on a 1-GPU box: every rank uses device 0 (gloo for the setup exchange; the strips then map "
-                         "each other's memory through CUDA IPC on the same device)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    if args.one_gpu:
-        local = 0
     torch.cuda.set_device(local)
     from qcnn_gpu_b200.host import numa
     numa.bind_to_gpu(local)
-    cdev = "cpu" if args.one_gpu else "cuda"            # where the tensors of the (setup / report) collectives live
+    cdev = "cuda"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if args.one_gpu:
-            dist.init_process_group("gloo")
-        else:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     h, w = args.height, args.width
     model = synth.make_model(0xC0FFEE + args.qp, args.qp)
     image = formats.write_model_vect_c(model)

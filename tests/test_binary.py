@@ -39,7 +39,7 @@ def test_library_is_sm_100a_only(sass):
 def test_fused_kernel_uses_tcgen05_and_parks_its_waiters(sass):
     _, kernels = sass
     fused = {k: v for k, v in kernels.items() if "k_fused" in k}
-    assert len(fused) == 3, list(fused)                      # FAST, generic requantiser, FAST + profiling
+    assert len(fused) == 5, list(fused)                      # {FAST, generic requantiser} x {whole frames, row window} + FAST profiling
     for name, lines in fused.items():
         text = "\n".join(lines)
         assert len(re.findall(r"\bUTCIMMA\b", text)) == 27, name        # the 27 MMAs of one row iteration, unrolled once

@@ -108,3 +108,31 @@ def test_cli_stream_mode(tmp_path, models):
     assert np.array_equal(raw[:, :h * w].reshape(frames, h, w), want)
     (psnr2,) = struct.unpack("<d", (tmp_path / "recon_psnr.data").read_bytes())
     assert psnr2 == oracle.psnr(want, ori)[0]
+
+
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "qcnn_ref_driver_on_shim")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="oracle/_ref/qcnn_ref_driver_on_shim not built (needs /root/reference at build time)")
+def test_reference_driver_compiled_against_the_shim(tmp_path, models):
+    """The reference's OWN driver text -- testqvrcnn / run_all / main, inference/kernel.cu:74-138, extracted verbatim at
+    build time by oracle/ref_witness/Makefile -- compiled against this repository's qvrcnn.cuh / yuv_data.h and linked with
+    libqvrcnn_b200.so: same argv, same per-frame sequence (load_data, forward_blu, cudaMemcpy of I1.x_rec), same report
+    and appended files, results equal to the oracle's."""
+    from oracle import oracle
+    qp, h, w = 22, 72, 136                                  # run_all only loops qp = 22 (kernel.cu:122), FRAME = 1
+    anchor, ori = synth.make_frames(0xC0FFEE + 14, 1, h, w)
+    _write_yuv(tmp_path / "ori.yuv", ori, 0x80)
+    _write_yuv(tmp_path / ("anchor_Q%d.yuv" % qp), anchor, 0x33)
+    image = formats.write_model_vect_c(models[qp])
+    (tmp_path / ("qvrcnn_nchw_vect_c_8bit_qfp_%d.data" % qp)).write_bytes(image)
+    p = subprocess.run([REF_DRIVER, "ori.yuv", "anchor_", str(h), str(w)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    want = oracle.OracleModel(image).forward_blu(anchor)
+    before = float(re.search(r"before net:PSNR=([0-9.]+)", p.stdout).group(1))
+    after = float(re.search(r"after quantized net:PSNR=([0-9.]+)", p.stdout).group(1))
+    assert before == pytest.approx(round(oracle.psnr(anchor, ori)[0], 3), abs=1.1e-3)
+    assert after == pytest.approx(round(oracle.psnr(want, ori)[0], 3), abs=1.1e-3)
+    (psnr2,) = struct.unpack("<d", (tmp_path / "recon_psnr.data").read_bytes())
+    assert psnr2 == oracle.psnr(want, ori)[0]                # bit-identical frame => bit-identical double
+    assert "after quantized net:PSNR=" in (tmp_path / "log.txt").read_text()

@@ -114,6 +114,21 @@ def test_hwcn_to_vect_c_converter_matches_python(tmp_path, models):
         api.convert_model_hwcn_to_vect_c(str(tmp_path / "nope"), str(fout))
 
 
+@pytest.mark.parametrize("qp", [27, 32])
+def test_hwcn_to_vect_c_converter_matches_the_reference_converter(tmp_path, qp):
+    """Golden produced by the reference's OWN model_qfp_HWCN2NCHW_VECT_C (inference/qvrcnn.cu:558-585 ->
+    HWCN2NCHW_VECT_C_CPU, inference/mat.cu:97-119), compiled unmodified into oracle/_ref/qcnn_ref_convert and run by
+    tests/golden/make_converter_golden.py: same HWCN file in, byte-identical NCHW_VECT_C file out."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_converter_qp%d.npz" % qp))
+    fin, fout = tmp_path / "hwcn.data", tmp_path / "vect_c.data"
+    fin.write_bytes(g["hwcn"].tobytes())
+    api.convert_model_hwcn_to_vect_c(str(fin), str(fout))
+    assert fout.read_bytes() == g["vect_c"].tobytes()
+    # and the python-side writers used by every other test agree with the reference's bytes
+    m = formats.read_model_hwcn(g["hwcn"].tobytes())
+    assert formats.write_model_vect_c(m) == g["vect_c"].tobytes()
+
+
 def test_yuv_io_and_psnr(tmp_path):
     anchor, ori = synth.make_frames(7, 3, 18, 34)
     # a "real" 4:2:0 file: Y then non-zero chroma the reader must skip (inference/yuv_data.cpp:32-38)

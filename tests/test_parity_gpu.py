@@ -149,6 +149,78 @@ def test_fused_equals_layered_1080p(models):
     assert np.array_equal(out_f[0], _oracle(m).forward_blu(anchor[0:1])[0])
 
 
+def test_config3_all_64_distinct_frames(models):
+    """BASELINE config 3 at full size with 64 DISTINCT frames (the bench tiles 8): the two independently written CUDA
+    implementations agree on every one of them, the oracle pins three, and every frame differs from its input."""
+    m = models[32]
+    anchor, _ = synth.make_frames(0xC0FFEE + 40, 64, 1080, 1920)
+    net = _net(m, 8, 1080, 1920, api.IMPL_LAYERED)
+    out_l = net.forward_frames_host(anchor)
+    _fused_or_skip(net, api.IMPL_FUSED)
+    net.set_impl(api.IMPL_FUSED)
+    out_f = net.forward_frames_host(anchor)
+    assert np.array_equal(out_l, out_f)
+    pick = [0, 37, 63]
+    assert np.array_equal(out_f[pick], _oracle(m).forward_blu(anchor[pick]))
+    assert all((out_f[i] != anchor[i]).any() for i in range(64))
+    assert len({hashlib.sha256(out_f[i].tobytes()).hexdigest() for i in range(64)}) == 64
+
+
+def test_hwcn_model_file_loads_to_the_same_network(models, tmp_path):
+    """qv_load_static_para_hwcn (the TF-side HWCN dump, input of model_qfp_HWCN2NCHW_VECT_C, inference/qvrcnn.cu:535-585)
+    gives the same network as the converted NCHW_VECT_C file: on the reference's own converter golden and on a fresh model,
+    both CUDA paths."""
+    g = np.load(os.path.join(GOLDEN, "ref_converter_qp32.npz"))
+    fin = tmp_path / "hwcn.data"
+    fin.write_bytes(g["hwcn"].tobytes())
+    anchor, _ = synth.make_frames(0xC0FFEE + 41, 2, 90, 200)
+    a = api.QVRCNN(0, 2, 1, 90, 200)
+    a.load_static_para_hwcn(str(fin))
+    b = api.QVRCNN(0, 2, 1, 90, 200)
+    b.load_static_para_mem(g["vect_c"].tobytes())               # what the REFERENCE's converter wrote
+    want = _oracle(formats.read_model_vect_c(g["vect_c"].tobytes())).forward_blu(anchor)
+    for impl in IMPLS:
+        a.set_impl(impl); b.set_impl(impl)
+        assert np.array_equal(a.forward_frames_host(anchor), want)
+        assert np.array_equal(b.forward_frames_host(anchor), want)
+    assert a.quant_params().tolist() == b.quant_params().tolist()
+    with pytest.raises(api.QVError):
+        a.load_static_para_hwcn(str(tmp_path / "missing.data"))
+    short = tmp_path / "short.data"
+    short.write_bytes(g["hwcn"].tobytes()[:-1])
+    with pytest.raises(api.QVError):
+        a.load_static_para_hwcn(str(short))
+
+
+def test_two_threads_load_and_run_two_handles_concurrently(models):
+    """include/qvrcnn_b200.h: "distinct handles may be used from distinct threads" -- including the model upload (the
+    operand table in constant memory is written once per device under a lock; `qcnn_gpu --gpus N` is this pattern)."""
+    import threading
+    imgs = {qp: formats.write_model_vect_c(models[qp]) for qp in (22, 37)}
+    frames = {22: synth.make_frames(0xC0FFEE + 42, 3, 120, 250)[0], 37: synth.make_frames(0xC0FFEE + 43, 3, 120, 250)[0]}
+    got, errs = {}, []
+    gate = threading.Barrier(2)
+
+    def work(qp):
+        try:
+            for rep in range(3):
+                gate.wait(timeout=60)
+                net = api.QVRCNN(0, 3, 1, 120, 250)
+                net.load_static_para_mem(imgs[qp])
+                got[(qp, rep)] = net.forward_frames_host(frames[qp])
+                net.close()
+        except Exception as e:            # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=work, args=(qp,)) for qp in (22, 37)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert not errs, errs
+    for qp in (22, 37):
+        want = _oracle(models[qp]).forward_blu(frames[qp])
+        for rep in range(3):
+            assert np.array_equal(got[(qp, rep)], want), (qp, rep)
+
+
 def test_full_size_properties_4k_and_8k(models):
     """BASELINE configs 4 and 5 at their real frame sizes, through properties that need no CPU oracle run:
     (a) 3840x2160, QP 27: frames are independent -- a frame inside a batch of 3 equals the same frame processed alone,

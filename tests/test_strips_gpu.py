@@ -1,10 +1,10 @@
 """One frame over several strips with peer-mapped halo rows (qv_strip_*), bit for bit against the
 whole-frame result and the oracle.
 
-On a 1-GPU box the strips share device 0 -- same process (peer = plain pointer) and separate processes (CUDA IPC on one
-device) -- which runs the whole protocol (two input slots, sequence words, acquire before reuse, halo rows read out of the
-neighbour's block) with the stream-level waits.  With >= 2 devices the same tests also run one strip per GPU: peer
-access / IPC over NVLink and the waits inside the fused kernel.  Both through the ctypes binding and through the C++
+On a 1-GPU box the strips share device 0 in one process (peer = plain pointer), which runs the whole protocol (two input
+slots, sequence words, acquire before reuse, halo rows read out of the neighbour's block) with the stream-level, bounded
+waits.  With >= 2 devices the same tests also run one strip per GPU -- peer access in one process, CUDA IPC between
+processes, over NVLink -- with the waits inside the fused kernel.  Both through the ctypes binding and through the C++
 driver (`qcnn_gpu --strips`, `qcnn_gpu --gpus N`)."""
 import json
 import os
@@ -58,32 +58,28 @@ def _strip_nets(image, h, w, bounds, devices):
     return nets
 
 
-def _run_strips(nets, bounds, frames, w):
-    """frames [K,h,w]: K steps, slot k&1, every handle enqueues step k before anyone is waited for."""
+def _run_strips(nets, bounds, frames, w, devices):
+    """frames [K,h,w]: K steps, slot k&1.  Strips that share a device are driven on one stream, all loads of a frame before
+    its forwards (stream order is what orders them); strips on different devices have a stream each and the fused kernels
+    wait for each other's rows themselves."""
     import torch
     K = frames.shape[0]
     outs = [[] for _ in nets]
-    streams = []
-    for i, n in enumerate(nets):
-        with torch.cuda.device(n_dev(n)):
-            streams.append(torch.cuda.Stream())
+    streams = {}
+    for d in set(devices):
+        with torch.cuda.device(d):
+            streams[d] = torch.cuda.Stream()
     for k in range(K):
         for i, n in enumerate(nets):
-            with torch.cuda.device(n_dev(n)):
+            n.strip_load(k & 1, frames[k, bounds[i]:bounds[i + 1]], streams[devices[i]].cuda_stream)
+        for i, n in enumerate(nets):
+            with torch.cuda.device(devices[i]):
                 o = torch.empty((bounds[i + 1] - bounds[i], w), dtype=torch.uint8, device="cuda")
-                n.strip_load(k & 1, frames[k, bounds[i]:bounds[i + 1]], streams[i].cuda_stream)
-                n.strip_forward(k & 1, o.data_ptr(), streams[i].cuda_stream)
-                outs[i].append(o)
+            n.strip_forward(k & 1, o.data_ptr(), streams[devices[i]].cuda_stream)
+            outs[i].append(o)
     for i, n in enumerate(nets):
-        n.synchronize(streams[i].cuda_stream)
+        n.synchronize(streams[devices[i]].cuda_stream)
     return np.stack([np.concatenate([outs[i][k].cpu().numpy() for i in range(len(nets))]) for k in range(K)])
-
-
-_DEV = {}
-
-
-def n_dev(net):
-    return _DEV[id(net)]
 
 
 @pytest.mark.parametrize("layout", ["one_device", "one_strip_per_device"])
@@ -98,14 +94,18 @@ def test_strips_equal_whole_frame_and_oracle(models, layout):
     image = formats.write_model_vect_c(models[qp])
     frames, _ = synth.make_frames(0xC0FFEE + 31, K, h, w)
     nets = _strip_nets(image, h, w, bounds, devices)
-    for n, d in zip(nets, devices):
-        _DEV[id(n)] = d
-    got = _run_strips(nets, bounds, frames, w)
+    got = _run_strips(nets, bounds, frames, w, devices)
     whole = api.QVRCNN(0, 1, 1, h, w)
     whole.load_static_para_mem(image)
     want = whole.forward_frames_host(frames)
     assert np.array_equal(got, want), "strips differ from the whole frame in %d pixels" % int((got != want).sum())
     assert np.array_equal(want[:2], oracle.OracleModel(image).forward_blu(frames[:2]))
+    if layout == "one_device":
+        # strips that share a GPU must share the stream: a second stream is refused, not raced
+        import torch
+        other = torch.cuda.Stream()
+        with pytest.raises(api.QVError, match="ONE caller-provided stream"):
+            nets[1].strip_load(0, frames[0, bounds[1]:bounds[2]], other.cuda_stream)
     for n in nets:
         n.strip_release()
 
@@ -123,6 +123,9 @@ def test_strip_api_refuses_what_it_cannot_do(models):
     o = torch.empty((20, w), dtype=torch.uint8, device="cuda")
     with pytest.raises(api.QVError, match="no neighbour attached"):
         a.strip_forward(0, o.data_ptr())
+    a.strip_attach(api.STRIP_BELOW, b.strip_export())
+    with pytest.raises(api.QVError, match="has not filled slot"):          # same GPU: loads of a frame come before its forwards
+        a.strip_forward(0, o.data_ptr())
     with pytest.raises(api.QVError, match="not adjacent"):
         a.strip_attach(api.STRIP_ABOVE, b.strip_export())
     with pytest.raises(api.QVError, match="not a strip descriptor"):
@@ -139,8 +142,12 @@ def test_strip_api_refuses_what_it_cannot_do(models):
     e.strip_setup(h, 0, h)
     x, _ = synth.make_frames(5, 1, h, w)
     oo = torch.empty((h, w), dtype=torch.uint8, device="cuda")
-    e.strip_load(0, x[0])
-    e.strip_forward(0, oo.data_ptr())
+    st = torch.cuda.Stream()
+    for n in (a, b, c, d):
+        n.strip_release()
+    e.strip_load(0, x[0], st.cuda_stream)
+    e.strip_forward(0, oo.data_ptr(), st.cuda_stream)
+    e.synchronize(st.cuda_stream)
     assert np.array_equal(oo.cpu().numpy(), e.forward_frames_host(x)[0])
 
 
@@ -197,17 +204,15 @@ def _torchrun(nproc, extra, timeout=600):
     return json.loads(line)
 
 
-@pytest.mark.parametrize("layout", ["one_gpu_ipc", "one_rank_per_gpu"])
-def test_multiprocess_strips_bit_identical(layout):
-    """One process per strip (the bench's launch shape): the neighbours' blocks are mapped through CUDA IPC; every step of
-    the check uploads a different frame, alternating the input slots; rank 0 recomputes every frame alone."""
-    if layout == "one_rank_per_gpu" and _ndev() < 2:
+def test_multiprocess_strips_bit_identical():
+    """One process per GPU (the bench's launch shape): the neighbours' blocks are mapped through CUDA IPC and the fused kernel
+    waits for their rows itself; every step of the check uploads a different frame, alternating the input slots; rank 0
+    recomputes every frame alone.  (Never several ranks on ONE GPU: kernels of different processes that wait for each
+    other are not guaranteed to run at the same time -- qv_strip_attach refuses that layout.)"""
+    if _ndev() < 2:
         pytest.skip("needs 2 devices")
-    nproc = 2 if layout == "one_gpu_ipc" else min(_ndev(), 8)
-    extra = ["--mode", "strips", "--qp", "22", "--height", "270", "--width", "480", "--steps", "6", "--check"]
-    if layout == "one_gpu_ipc":
-        extra.append("--one-gpu")
-    r = _torchrun(nproc, extra)
+    nproc = min(_ndev(), 8)
+    r = _torchrun(nproc, ["--mode", "strips", "--qp", "22", "--height", "270", "--width", "480", "--steps", "6", "--check"])
     assert r["bit_identical_to_1gpu"] is True and r["distinct_frames_checked"] == 6, r
     assert r["n_gpus"] == nproc
 
