@@ -561,8 +561,13 @@ def main():
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": npx, "d2h_bytes_per_step": npx,
                     "api": "qv_forward_frames_host (pinned host in/out)", "bit_identical_to_device_path": same,
+                    # what could bind the end-to-end rate: the kernels (device-resident rate) or the host side (the box's
+                    # measured concurrent pinned-copy rate, 1 byte per pixel each way)
                     "copy_ceiling": ceiling, "copy_gbs_each_way": e2e_mpx * 1e6 / 1e9,
                     "frac_of_copy_ceiling": e2e_mpx * 1e6 / 1e9 / ceiling["h2d_plus_d2h_concurrent_gbs_each_way"],
+                    "frac_of_device_rate": e2e_mpx / value,
+                    "bound": "copies (host memory / PCIe)" if ceiling["h2d_plus_d2h_concurrent_gbs_each_way"] * 1e3 < value else "kernel",
+                    "frac_of_binding_limit": e2e_mpx / min(value, ceiling["h2d_plus_d2h_concurrent_gbs_each_way"] * 1e3),
                     "numa": numa_info, "reference_call_pattern": per_frame},
             "roofline": {"bound": "tensor", "achieved": tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": tops / int8_peak,
                          "traffic": ncu_traffic(), "peak_source": "2 x bf16_tflops (burst), " + peaks["source"],

@@ -69,6 +69,9 @@
 #ifndef QV_EXP
 #define QV_EXP 0
 #endif
+#ifndef QV_LIGHT_PROF
+#define QV_LIGHT_PROF 0          // profiling build: 1 = only the timeline of block 0 (no per-MMA stamps, no per-thread counters)
+#endif
 
 namespace qv {
 namespace {
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     const long long t = clock64(); t_wait += t - tc0; tc0 = t;
                     tr = P.dbg && leader && unit == 0 && i >= TR_ITER0 && i < TR_ITER0 + TR_N;
                     if (tr) P.dbg[gridDim.x * 16 + (i - TR_ITER0) * 16 + 0] = tc0;
-                    stamp = tr ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
+                    stamp = (tr && !QV_LIGHT_PROF) ? P.dbg + gridDim.x * 16 + TR_N * 16 + (i - TR_ITER0) * 32 : nullptr;
                 }
                 // ---- C1: a1 row R1 = im2col stage (R1 mod 3) x W1 (N = 64) -------------------------------
                 MMA(ONCE, op.d1, 0, idesc_i8(128, 64), 0);
@@ -395,7 +398,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         long long tw[6] = {0, 0, 0, 0, 0, 0}, tc0 = PROF ? clock64() : 0, t_ldtm = 0;
         int tr_slot = -1;                                         // timeline trace (QV_FUSED_PROFILE): block 0, first unit, a few iterations
         auto lap = [&](int k) {
-            if (PROF) {
+            if (PROF && QV_LIGHT_PROF) {
+                if (tr_slot >= 0 && k < 4) P.dbg[gridDim.x * 16 + tr_slot + k] = clock64();
+            } else if (PROF) {
                 const long long t = clock64(); tw[k] += t - tc0; tc0 = t;
                 if (tr_slot >= 0 && k < 4) P.dbg[gridDim.x * 16 + tr_slot + k] = t;
             }

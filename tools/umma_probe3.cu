@@ -457,6 +457,70 @@ static void burst_case(long long *dC, int *dSt)
     printf("burst N=%3d k=%2d MMAs: issued after %lld cycles, complete (commit seen) after %lld  timeout=%d\n", N, K, c[0], c[1], st);
 }
 
+
+// ---- two issuing threads: is the ~46-cycle issue cost of an MMA a property of the issuing THREAD (then two warps could feed
+// ---- the tensor pipe twice as fast with small MMAs) or of the pipe's front end?  NW warps (on different SM sub-partitions)
+// ---- each issue K MMAs of width N into their own TMEM region, own B tile, own A tile; REUSE = every second MMA takes A from
+// ---- the collector (fill / lastuse pairs).  Reported: cycles until ALL commits are seen, per MMA.
+template <int NW, int K, int N, int REUSE>
+__global__ void k_dual(long long *cycles, int *status)
+{
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sA = sm, *sB = sm + 32768;
+    __shared__ uint64_t bar[4];
+    __shared__ uint32_t s_tmem;
+    __shared__ long long s_t[4][2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (32768 + 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sm)[i] = 0x01010101u * (i & 3);
+    fence_proxy_async_smem();
+    if (tid == 0) { for (int w = 0; w < 4; ++w) mbar_init(&bar[w], 1); mbar_fence_init(); }
+    if (warp == 0) { tmem_alloc(&s_tmem, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = s_tmem;
+    if (warp < NW && lane == 0) {
+        constexpr uint32_t id = idesc_i8(128, N, 1, 1);
+        const uint64_t bd = smem_desc(smem_u32(sB + warp * 4096), 128 * 16, 128);
+        const uint64_t ad0 = smem_desc(smem_u32(sA + warp * 8192), 4096, 128);
+        const uint32_t d = tm + warp * 128;
+        long long t0 = clock64();
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (REUSE) { if (j & 1) mma_col<3>(d, ad0, bd, id, 1); else mma_col<1>(d, ad0, bd, id, 1); }
+            else mma_col<0>(d, ad0 + (uint64_t)((j * 37) % 200), bd, id, 1);
+        }
+        long long t1 = clock64();
+        mma_commit(&bar[warp]);
+        const bool ok = mbar_wait(&bar[warp], 0);
+        long long t2 = clock64();
+        s_t[warp][0] = t1 - t0; s_t[warp][1] = t2 - t0;
+        if (!ok) status[0] = 1;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        long long a = 0, b = 0;
+        for (int w = 0; w < NW; ++w) { a = max(a, s_t[w][0]); b = max(b, s_t[w][1]); }
+        cycles[0] = a; cycles[1] = b;
+    }
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+template <int NW, int K, int N, int REUSE>
+static void dual_case(long long *dC, int *dSt)
+{
+    CK(cudaFuncSetAttribute(k_dual<NW, K, N, REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 16384));
+    long long c[2]; int st = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaMemset(dSt, 0, 4));
+        k_dual<NW, K, N, REUSE><<<1, 128, 32768 + 16384>>>(dC, dSt);
+        CK(cudaDeviceSynchronize());
+    }
+    CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dSt, 4, cudaMemcpyDeviceToHost));
+    printf("dual  %d issuing warp(s) x %2d MMAs N=%3d %-22s: issue %.1f cyc/MMA/warp, all complete after %lld = %.1f cyc per MMA overall  timeout=%d\n", NW, K, N,
+           REUSE ? "(A fill/lastuse pairs)" : "(A from smem each)", (double)c[0] / K, c[1], (double)c[1] / (K * NW), st);
+}
+
 // ---- handshake latencies: what one leg of the MMA-warp / worker ping-pong costs ---------------------------------------
 // mode 0: pure mbarrier ping-pong between warp 0 and warp 1 (arrive -> try_wait sees it), round trip / 2
 // mode 1: warp 0 issues one small MMA (N = 16) + tcgen05.commit, warp 1 waits for the commit and arrives back
@@ -589,6 +653,15 @@ int main(int argc, char **argv)
         burst_case<1, 128>(dC, dSt); burst_case<2, 128>(dC, dSt); burst_case<4, 128>(dC, dSt); burst_case<8, 128>(dC, dSt);
         burst_case<16, 128>(dC, dSt); burst_case<32, 128>(dC, dSt); burst_case<64, 128>(dC, dSt);
         burst_case<1, 32>(dC, dSt); burst_case<4, 32>(dC, dSt); burst_case<8, 32>(dC, dSt); burst_case<16, 32>(dC, dSt); burst_case<32, 32>(dC, dSt);
+    }
+    if (!strcmp(t, "dual")) {
+        long long *dC; int *dSt;
+        CK(cudaMalloc(&dC, 64)); CK(cudaMalloc(&dSt, 4));
+        dual_case<1, 32, 16, 0>(dC, dSt); dual_case<2, 16, 16, 0>(dC, dSt); dual_case<2, 32, 16, 0>(dC, dSt); dual_case<4, 16, 16, 0>(dC, dSt);
+        dual_case<1, 32, 16, 1>(dC, dSt); dual_case<2, 16, 16, 1>(dC, dSt); dual_case<2, 32, 16, 1>(dC, dSt);
+        dual_case<1, 32, 64, 0>(dC, dSt); dual_case<2, 16, 64, 0>(dC, dSt); dual_case<2, 32, 64, 0>(dC, dSt);
+        dual_case<1, 32, 64, 1>(dC, dSt); dual_case<2, 32, 64, 1>(dC, dSt);
+        dual_case<1, 32, 128, 0>(dC, dSt); dual_case<2, 32, 128, 0>(dC, dSt); dual_case<2, 32, 128, 1>(dC, dSt);
     }
     if (!strcmp(t, "cont2")) {
         long long *dC; int *dSt;
