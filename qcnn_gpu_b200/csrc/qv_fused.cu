@@ -59,6 +59,7 @@
 #include <type_traits>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "qv_device.cuh"
@@ -107,6 +108,11 @@ constexpr int OFF_A3 = (OFF_IN + IN_SLOTS * IN_PITCH + 15) / 16 * 16;   // a3 ro
 constexpr int OFF_CTRL = OFF_A3 + A_SLOTS * A2_ROW;
 constexpr int SMEM_BYTES = OFF_CTRL + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+// TMA variant of the input ring (QV_FUSED_TMA): rows land by cp.async.bulk.tensor, whose destination must be 128-byte aligned
+constexpr int IN_PITCH_T = 256, IN_BOX = 144;
+constexpr int OFF_IN_T = (SMEM_BYTES + 127) / 128 * 128;
+constexpr int SMEM_BYTES_T = OFF_IN_T + IN_SLOTS * IN_PITCH_T;
+static_assert(SMEM_BYTES_T <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
 constexpr int NWORKER = 256, NC4 = 128, NTHREADS = NWORKER + 32 + NC4;   // warps 0-7 workers, 8 MMA issue, 9-12 C4
 constexpr int TR_ITER0 = 300, TR_N = 8;    // profile-mode timeline window
@@ -127,7 +133,8 @@ struct GroupQ {
     int blu, mul, shift, rbias;   // generic path: the reference formula verbatim
 };
 
-struct FusedParams {
+struct alignas(64) FusedParams {
+    CUtensorMap tmap_in;               // TMA variant: the input as a 2-D byte tensor {W, n_frames * H}, box {IN_BOX, 1}
     // Row r of frame f is read at in + f*frame_stride + r*W and written at out + f*frame_stride + r*W: `in` / `out` are
     // VIRTUAL bases (buffer pointer minus first-row offset) when the buffers hold only a row window of the image.
     const uint8_t *in;
@@ -272,9 +279,14 @@ __device__ __forceinline__ void c4_taps(const uint4 (&v)[3], const FusedParams &
 // ROWS: the launch covers a row window of one frame (strips over several GPUs).  The whole-frame instantiation keeps
 // the plain addressing: every instruction the C4 warps spend on the input ring is taken from the MMA warp's issue slots
 // (same SM sub-partition), and the window arithmetic cost 2.5 % at 64 x 1080p (profiles/r2_kernel_ab_rowwindow.log).
-template <bool FAST, bool PROF, bool ROWS>
+// TMA: the input ring is filled by cp.async.bulk.tensor.2d (one elected thread, one 144-byte box per row, completion on an
+// mbarrier) instead of per-thread byte loads and stores.  TMA pads out-of-image columns with 0 where the net needs 128 (0 in
+// the x - 128 domain), so edge strips patch those bytes after the row has landed, and out-of-image rows are filled by hand.
+template <bool FAST, bool PROF, bool ROWS, bool TMA = false>
 __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ FusedParams P)
 {
+    static_assert(!(TMA && ROWS), "the TMA input ring exists for whole-frame launches only");
+    constexpr int IN_BASE = TMA ? OFF_IN_T : OFF_IN, IN_ROWPITCH = TMA ? IN_PITCH_T : IN_PITCH;
     extern __shared__ __align__(1024) uint8_t sm[];
     // MMA warp (tcgen05.commit) -> workers: two mbarriers used alternately (event e -> barrier e&1, parity (e>>1)&1).  A
     // waiter can then never be lapped: the second-next completion of the SAME barrier needs the waiter's own arrival
@@ -292,9 +304,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         reinterpret_cast<uint4 *>(sm)[i] = reinterpret_cast<const uint4 *>(P.wimg)[i];
     for (int i = tid; i < (OFF_CTRL - OFF_A1) / 16; i += NTHREADS)      // finite data everywhere the MMAs may read
         reinterpret_cast<uint4 *>(sm + OFF_A1)[i] = make_uint4(0, 0, 0, 0);
+    uint64_t *bar_in = reinterpret_cast<uint64_t *>(sm + OFF_CTRL + 40);       // TMA variant: input rows landed (two, alternating)
     if (tid == 0) {
         mbar_init(&bar_mma[0], 1);
         mbar_init(&bar_mma[1], 1);
+        if (TMA) { mbar_init(&bar_in[0], 1); mbar_init(&bar_in[1], 1); }
         *s_fail = 0;
         mbar_fence_init();
     }
@@ -504,7 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         // the output rows r+1 (dy = 0), r (dy = 1) and r-1 (dy = 2); two running sums carry the partial rows, and row
         // r-1 = R1-10 is complete: applyRes_y (cnn.cu:507-523) and the store.
         const int mo = tid - (NWORKER + 32);
-        uint32_t ev_work = 0;
+        uint32_t ev_work = 0, tma_n = 0;
         auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
@@ -527,10 +541,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 const unsigned b = (rok && ok_b) ? (unsigned)rp[col_b] : 128u;
                 return a | (b << 8);
             };
+            // TMA boxes must start on a 16-byte boundary of the tensor (measured: anything else is an illegal instruction,
+            // profiles/r2_tma_probe.log); X0 - 8 is a multiple of 8, so the box starts in_sh = 0 or 8 bytes early and the ring
+            // rows of this unit are simply read in_sh bytes further right
+            const int in_sh = TMA ? ((X0 - 8) & 15) : 0;
             auto store_in = [&](int row, unsigned v) {
-                uint8_t *rp = sm + OFF_IN + ((row + 4096) & (IN_SLOTS - 1)) * IN_PITCH;
+                uint8_t *rp = sm + IN_BASE + in_sh + ((row + 4096) & (IN_SLOTS - 1)) * IN_ROWPITCH;
                 rp[mo] = (uint8_t)v;
                 if (mo < PW - 128) rp[128 + mo] = (uint8_t)(v >> 8);
+            };
+            // TMA variant: one thread asks for image row `row` of this frame (columns X0-8 .. X0+135; out-of-image columns
+            // arrive as 0), `tx` bytes are expected on barrier `b` in total
+            const bool edge = X0 == 0 || X0 - 8 + PW > W;
+            auto tma_expect = [&](int b, uint32_t tx) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_in[b])), "r"(tx) : "memory");
+            };
+            auto tma_row = [&](int row, int b) {
+                const uint32_t dst = smem_u32(sm + IN_BASE + ((row + 4096) & (IN_SLOTS - 1)) * IN_ROWPITCH);
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(dst), "l"(&P.tmap_in), "r"(X0 - 8 - in_sh), "r"(f * H + row), "r"(smem_u32(&bar_in[b])) : "memory");
+            };
+            auto patch_edges = [&](int row) {                      // 128 where the image ends (TMA wrote 0 there)
+                uint8_t *rp = sm + IN_BASE + in_sh + ((row + 4096) & (IN_SLOTS - 1)) * IN_ROWPITCH;
+                if (!ok_a) rp[mo] = 128;
+                if (mo < PW - 128 && col_b >= W) rp[128 + mo] = 128;
             };
             // im2col of input rows R-2..R+2 for a1 row R (pixel m = mo), the A operand of C1
             const int m = mo;
@@ -539,7 +573,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                 const int p = m + 2, o8 = (p & 3) * 8;
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
-                    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm + OFF_IN + ((R + 4094 + r) & (IN_SLOTS - 1)) * IN_PITCH) + (p >> 2);
+                    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm + IN_BASE + in_sh + ((R + 4094 + r) & (IN_SLOTS - 1)) * IN_ROWPITCH) + (p >> 2);
                     const uint32_t w0 = rowp[0], w1 = rowp[1];
                     A[r] = __funnelshift_r(w0, w1, o8);           // bytes p..p+3   (taps s = 0..3)
                     const uint32_t b = (w1 >> o8) & 0xffu;        // byte  p+4      (tap  s = 4)
@@ -556,7 +590,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             if (ROWS && P.flag_top && y0 - 6 < P.own0 && P.rlo < P.own0) { if (lane == 0 && !peer_wait(P.flag_top, P.seq)) *s_fail = 3; __syncwarp(); }
             if (ROWS && P.flag_bot && y1 + PIPE > P.own1 && P.rhi > P.own1) { if (lane == 0 && !peer_wait(P.flag_bot, P.seq)) *s_fail = 3; __syncwarp(); }
             // ---- prologue: input rows for a1 rows y0-4 and y0-3, C1 operand of the first ------------
-            for (int r = y0 - 6; r <= y0 - 1; ++r) store_in(r, load_in(r));
+            if (TMA) {
+                const int r_lo = max(y0 - 6, 0), r_hi = min(y0, H);           // the rows of the six that exist
+                if (r_hi > r_lo) {
+                    if (mo == 0) {
+                        fence_proxy_async_smem();                  // the previous unit's reads of these slots (generic proxy) come first
+                        tma_expect(tma_n & 1, (uint32_t)(r_hi - r_lo) * IN_BOX);
+                        for (int r = r_lo; r < r_hi; ++r) tma_row(r, tma_n & 1);
+                    }
+                    warp_wait(&bar_in[tma_n & 1], (tma_n >> 1) & 1, lane, s_fail);
+                    ++tma_n;
+                    if (edge) for (int r = r_lo; r < r_hi; ++r) patch_edges(r);
+                }
+                for (int r = y0 - 6; r < y0; ++r) if (r < 0 || r >= H) store_in(r, 128u | (128u << 8));
+            } else {
+                for (int r = y0 - 6; r <= y0 - 1; ++r) store_in(r, load_in(r));
+            }
             worker_bar();
             im2col(y0 - 4, c3);
             fence_proxy_async_smem();
@@ -564,7 +613,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             ++ev_work;
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
-                const unsigned in_next = load_in(R1 + 4);         // prefetch; stored at the end of the iteration
+                const bool row_in = (unsigned)(R1 + 4) < (unsigned)H;
+                unsigned in_next = 128u | (128u << 8);
+                if (TMA) {
+                    if (row_in && mo == 0) { tma_expect(tma_n & 1, IN_BOX); tma_row(R1 + 4, tma_n & 1); }    // lands during the iteration
+                } else {
+                    in_next = load_in(R1 + 4);                    // prefetch; stored at the end of the iteration
+                }
                 // the C1 operand of the next iteration, stage (R1+1) mod 3: C1 of iteration i-2 (same stage) is complete,
                 // the workers saw its commit before the barrier that ended iteration i-1
                 if (i + 1 < niter) {
@@ -591,11 +646,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     c4_s1 = acc[0];
                     const int rowo = R1 - 10;
                     if (rowo >= y0 && rowo < y1 && col_ok) {
-                        const int x = sm[OFF_IN + ((R1p - 10) & (IN_SLOTS - 1)) * IN_PITCH + 8 + mo];
+                        const int x = sm[IN_BASE + in_sh + ((R1p - 10) & (IN_SLOTS - 1)) * IN_ROWPITCH + 8 + mo];
                         outf[(size_t)rowo * W + X0 + mo] = (uint8_t)residual_apply(u4 + P.c4_bias, x, P.c4_mul, P.c4_shift);   // cnn.cu:507-523
                     }
                 }
-                store_in(R1 + 4, in_next);
+                if (TMA && row_in) {
+                    warp_wait(&bar_in[tma_n & 1], (tma_n >> 1) & 1, lane, s_fail);
+                    ++tma_n;
+                    if (edge) patch_edges(R1 + 4);
+                } else {
+                    store_in(R1 + 4, in_next);
+                }
                 worker_bar();                                     // input ring complete for the next im2col; a3 rows of the workers visible
             }
             worker_bar();                                         // the workers' drain barrier
@@ -716,8 +777,9 @@ struct FusedModel {
     bool fast = true;
     int sm_count = 148;
     // environment switches, read once at upload (never on the per-launch path)
-    bool env_profile = false, env_test_fail = false;
+    bool env_profile = false, env_test_fail = false, env_tma = false;
     int env_experiment = 0;
+    void *encode_tiled = nullptr;      // cuTensorMapEncodeTiled (driver entry point; the library does not link libcuda)
 };
 
 // The operand table lives in constant memory: one copy per device, and its content depends only on the shared-memory
@@ -872,6 +934,7 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fused<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_T);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_bases, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     int dev = 0, sms = 148;
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
@@ -913,6 +976,13 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     fm->env_profile = getenv("QV_FUSED_PROFILE") != nullptr;
     fm->env_experiment = getenv("QV_FUSED_EXPERIMENT") ? atoi(getenv("QV_FUSED_EXPERIMENT")) : 0;
     fm->env_test_fail = getenv("QV_FUSED_TEST_FAIL") != nullptr;     // tests only: make every CTA report a base mismatch
+    fm->env_tma = getenv("QV_FUSED_TMA") != nullptr && atoi(getenv("QV_FUSED_TMA")) != 0;
+    if (fm->env_tma) {
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fm->encode_tiled, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+            fm->encode_tiled = nullptr;
+        cudaGetLastError();
+    }
     P.wimg = fm->d_wimg;
     P.fail_flag = nullptr;
     if (cudaHostAlloc(&fm->h_fail, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
@@ -1012,7 +1082,20 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     const size_t dbg_n = (size_t)grid * 16 + TR_N * 48;
     if (prof && !rows && cudaMalloc(&P.dbg, dbg_n * sizeof(long long)) != cudaSuccess) P.dbg = nullptr;
     if (P.dbg) cudaMemsetAsync(P.dbg, 0, dbg_n * sizeof(long long), st);
-    if (rows && fm->fast) k_fused<true, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
+    // TMA input ring (opt-in, QV_FUSED_TMA=1): whole-frame launches of the fast instantiation whose input can be described
+    // by a tensor map (16-byte aligned base and row pitch)
+    bool tma = false;
+    if (fm->env_tma && fm->encode_tiled && !rows && fm->fast && !P.dbg && W % 16 == 0 && W >= IN_BOX && ((uintptr_t)d_in & 15) == 0) {
+        using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)n * (cuuint64_t)H}, strides[1] = {(cuuint64_t)W};
+        const cuuint32_t box[2] = {(cuuint32_t)IN_BOX, 1}, estr[2] = {1, 1};
+        tma = reinterpret_cast<EncodeFn>(fm->encode_tiled)(&P.tmap_in, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(d_in), dims, strides, box, estr,
+                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (tma) k_fused<true, false, false, true><<<grid, NTHREADS, SMEM_BYTES_T, st>>>(P);
+    else if (rows && fm->fast) k_fused<true, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     else if (rows) k_fused<false, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     else if (fm->fast && P.dbg) k_fused<true, true, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);
     else if (fm->fast) k_fused<true, false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(P);

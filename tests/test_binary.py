@@ -39,7 +39,10 @@ def test_library_is_sm_100a_only(sass):
 def test_fused_kernel_uses_tcgen05_and_parks_its_waiters(sass):
     _, kernels = sass
     fused = {k: v for k, v in kernels.items() if "k_fused" in k}
-    assert len(fused) == 5, list(fused)                      # {FAST, generic requantiser} x {whole frames, row window} + FAST profiling
+    assert len(fused) == 6, list(fused)                      # {FAST, generic requantiser} x {whole frames, row window} + FAST profiling + FAST with the TMA input ring
+    tma = [k for k in fused if "ILb1ELb0ELb0ELb1E" in k]
+    assert len(tma) == 1 and "UTMALDG" in "\n".join(fused[tma[0]])        # cp.async.bulk.tensor.2d of the opt-in input ring
+    assert all("UTMALDG" not in "\n".join(v) for k, v in fused.items() if k != tma[0])
     for name, lines in fused.items():
         text = "\n".join(lines)
         assert len(re.findall(r"\bUTCIMMA\b", text)) == 27, name        # the 27 MMAs of one row iteration, unrolled once

@@ -363,6 +363,27 @@ def test_kernel_failure_is_reported(models, monkeypatch):
     assert np.array_equal(net.get_recon(), _oracle(models[32]).forward_blu(x))
 
 
+@pytest.mark.parametrize("shape", [(3, 40, 416), (2, 33, 144), (1, 70, 1920), (2, 21, 250)])
+def test_tma_input_ring_is_bit_identical(models, monkeypatch, shape):
+    """QV_FUSED_TMA=1 (read when the model is uploaded): the input ring filled by cp.async.bulk.tensor.2d -- boxes that start
+    16-byte aligned, out-of-image columns patched to 128, out-of-image rows filled by hand -- gives the same frames; a width
+    that is not a multiple of 16 cannot be described by a tensor map and silently takes the plain ring."""
+    n, h, w = shape
+    image = formats.write_model_vect_c(models[27])
+    x, _ = synth.make_frames(0xC0FFEE + 44, n, h, w)
+    a = api.QVRCNN(0, n, 1, h, w)
+    a.load_static_para_mem(image)
+    _fused_or_skip(a, api.IMPL_FUSED)
+    a.set_impl(api.IMPL_FUSED)
+    want = a.forward_frames_host(x)
+    monkeypatch.setenv("QV_FUSED_TMA", "1")
+    b = api.QVRCNN(0, n, 1, h, w)
+    b.load_static_para_mem(image)
+    b.set_impl(api.IMPL_FUSED)
+    assert np.array_equal(b.forward_frames_host(x), want)
+    assert np.array_equal(want[:1], _oracle(models[27]).forward_blu(x[:1]))
+
+
 def test_quant_param_file_plus_set_weights(models, tmp_path):
     """The shipped artefact is the per-QP scale file; weights come separately."""
     m = models[27]

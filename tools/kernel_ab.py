@@ -33,7 +33,11 @@ def main():
     outs = {}
     nets = {}
     for p in args.libs:
-        L = C.CDLL(os.path.abspath(p))
+        # "lib.so@KEY=VAL": the same library with an environment switch that is read when the model is uploaded
+        path, _, env = p.partition("@")
+        if env:
+            os.environ[env.split("=")[0]] = env.split("=")[1]
+        L = C.CDLL(os.path.abspath(path))
         L.qv_last_error.restype = C.c_char_p
         L.qv_create.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_void_p)]
         L.qv_load_static_para_mem.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -41,6 +45,8 @@ def main():
         h = C.c_void_p()
         assert L.qv_create(0, 8, 1, H, W, C.byref(h)) == 0, L.qv_last_error()
         assert L.qv_load_static_para_mem(h, image, len(image)) == 0, L.qv_last_error()
+        if env:
+            del os.environ[env.split("=")[0]]
         nets[p] = (L, h)
     st = torch.cuda.Stream()
     torch.cuda.synchronize()
@@ -69,7 +75,7 @@ def main():
                 ref = d_out.clone()
             same = bool(torch.equal(ref, d_out))
             line = "%-40s rep %d: min %.3f  median %.3f  mean %.3f ms  (first 5: %s)  same_output=%s" % (
-                os.path.basename(p), rep, min(ms), float(np.median(ms)), float(np.mean(ms)), " ".join("%.2f" % x for x in ms[:5]), same)
+                os.path.basename(p)[:40], rep, min(ms), float(np.median(ms)), float(np.mean(ms)), " ".join("%.2f" % x for x in ms[:5]), same)
             if args.sustained:
                 ms2 = run(p, args.sustained, d_out)
                 line += "  | sustained %d steps: mean %.3f, last quarter %.3f ms" % (args.sustained, float(np.mean(ms2)), float(np.mean(ms2[-len(ms2) // 4:])))
