@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
 #include <unistd.h>
 
 #include <cuda_runtime.h>
@@ -860,8 +861,11 @@ int qv_stream_yuv(qv_net *net, const char *anchor_yuv, const char *ori_yuv, cons
     if (!fa) { set_error("open file failed. (%s)", anchor_yuv); return QV_ERR_IO; }                       // yuv_data.cpp:19-31
     if (ori_yuv && !fo) { fclose(fa); set_error("open file failed. (%s)", ori_yuv); return QV_ERR_IO; }
     if (recon_yuv) {
-        fr = fopen(recon_yuv, "r+b");                       // several ranks may fill one file, each its own frame range
-        if (!fr) fr = fopen(recon_yuv, "w+b");
+        // several ranks / threads may fill one file, each its own frame range: open without truncating, create if missing
+        // (a second caller that lost the race to create it must not wipe what the first has written)
+        const int fd = open(recon_yuv, O_CREAT | O_RDWR, 0644);
+        fr = fd >= 0 ? fdopen(fd, "r+b") : nullptr;
+        if (!fr && fd >= 0) close(fd);
         if (!fr) { fclose(fa); if (fo) fclose(fo); set_error("open file failed. (%s)", recon_yuv); return QV_ERR_IO; }
     }
     StreamSlot slot[3];
