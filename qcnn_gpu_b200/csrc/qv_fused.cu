@@ -211,6 +211,36 @@ __device__ __forceinline__ bool peer_wait(const uint32_t *flag, uint32_t seq)
     return false;
 }
 
+// Row-window launches deal the work out by ROWS, not by whole segments: the nstrips x (ye - ys) row-iterations of the
+// launch form one line, CTA b takes [b * chunk, (b + 1) * chunk) of it, and that range is cut where it crosses into the next
+// strip column: unit = b + j * gridDim.x is the j-th piece.  (One 8K frame over 8 GPUs leaves 64 columns of 540 rows for 148
+// SMs: equal segments use 128 of them for 284 iterations, the line gives every SM 234 rows + the pipeline fill.)
+// ok = false for a piece that does not exist.
+struct UnitGeo { int strip, f, y0, y1; bool ok; };
+template <bool ROWS>
+__device__ __forceinline__ UnitGeo unit_geo(const FusedParams &P, int unit, int H)
+{
+    UnitGeo g;
+    if (!ROWS) {                       // whole frames: (frame, strip column, equal row segment)
+        const int seg = unit % P.nseg;
+        g.strip = (unit / P.nseg) % P.nstrips;
+        g.f = unit / (P.nseg * P.nstrips);
+        g.y0 = seg * P.seg_rows;
+        g.y1 = min(H, g.y0 + P.seg_rows);
+        g.ok = true;
+    } else {
+        const int R = P.ye - P.ys, b = unit % (int)gridDim.x, j = unit / (int)gridDim.x;
+        const int lo = b * P.seg_rows, hi = min(P.nstrips * R, lo + P.seg_rows), c0 = lo / R;
+        const int start = j == 0 ? lo : (c0 + j) * R, end = min(hi, (c0 + j + 1) * R);
+        g.strip = c0 + j;
+        g.f = 0;
+        g.y0 = P.ys + (start - g.strip * R);
+        g.y1 = g.y0 + (end - start);
+        g.ok = start < end;
+    }
+    return g;
+}
+
 // workers / C4 warps -> MMA warp, event ev: every lane arrives on named barrier 2 + ev mod 3, the MMA warp blocks in
 // bar.sync on the same id.  A warp blocked there issues nothing (a warp polling an mbarrier does, and on the MMA warp's SM
 // sub-partition that is measurable: DESIGN.md section 7) and is released ~40 cycles after the last arrival.  Three ids are
@@ -336,8 +366,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         if ((sbase >> 4) != P.sbase16 || tm != P.tmem_base) { if (lane == 0) *s_fail = 2; }     // c_ops does not describe this CTA
         const uint32_t r22 = tm + TM_R22, r21 = tm + TM_R21, r31 = tm + TM_R31;
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-            const int seg = unit % P.nseg;
-            const int y0 = (ROWS ? P.ys : 0) + seg * P.seg_rows, y1 = min(ROWS ? P.ye : H, y0 + P.seg_rows);
+            const UnitGeo g = unit_geo<ROWS>(P, unit, H);
+            if (ROWS && !g.ok) continue;
+            const int y0 = g.y0, y1 = g.y1;
             const int niter = y1 - y0 + PIPE;
             int ph = mod_pos(y0 - 4, N_PHASE);
             for (int i = 0; i < niter; ++i) {
@@ -421,9 +452,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         };
         auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };      // workers + C4 warps
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-            const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
+            const UnitGeo g = unit_geo<ROWS>(P, unit, H);
+            if (ROWS && !g.ok) continue;
+            const int strip = g.strip, f = g.f, y0 = g.y0, y1 = g.y1;
             const int X0 = strip * WT;
-            const int y0 = (ROWS ? P.ys : 0) + seg * P.seg_rows, y1 = min(ROWS ? P.ye : H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             // ---- prologue: the previous unit's accumulators are drained (nothing of this unit is in flight yet) ------------
             worker_bar();
@@ -521,9 +553,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         uint32_t ev_work = 0, tma_n = 0;
         auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-            const int seg = unit % P.nseg, strip = (unit / P.nseg) % P.nstrips, f = unit / (P.nseg * P.nstrips);
+            const UnitGeo g = unit_geo<ROWS>(P, unit, H);
+            if (ROWS && !g.ok) continue;
+            const int strip = g.strip, f = g.f, y0 = g.y0, y1 = g.y1;
             const int X0 = strip * WT;
-            const int y0 = (ROWS ? P.ys : 0) + seg * P.seg_rows, y1 = min(ROWS ? P.ye : H, y0 + P.seg_rows);
             const int niter = y1 - y0 + PIPE;
             const uint8_t *inf = P.in + (size_t)f * (ROWS ? P.frame_stride : (size_t)H * W);
             uint8_t *outf = P.out + (size_t)f * (ROWS ? P.frame_stride : (size_t)H * W);
@@ -1054,27 +1087,42 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
     }
     const int rows_out = P.ye - P.ys;
     P.nstrips = (W + WT - 1) / WT;
-    // Row segments.  Units are dealt to the persistent CTAs round-robin, so the makespan is
-    // ceil(units / SMs) * (rows per segment + PIPE) row-iterations; pick the cut that minimises it
-    // (never below 16 rows per segment: every segment pays PIPE iterations of pipeline fill).
-    const long long cols = (long long)n * P.nstrips;
-    int nseg = 1;
-    {
-        long long best = -1;
-        const int max_seg = std::max(1, std::min(rows_out / 16, 256));
-        for (int c = 1; c <= max_seg; ++c) {
-            const int rws = (rows_out + c - 1) / c, real = (rows_out + rws - 1) / rws;
-            const long long waves = (cols * real + fm->sm_count - 1) / fm->sm_count;
-            const long long cost = waves * (rws + PIPE);
-            if (best < 0 || cost < best) { best = cost; nseg = c; }
+    int grid = 1;
+    if (rows) {
+        // one line of nstrips * rows_out row-iterations, cut into equal chunks (rows_unit): every SM gets the same number
+        // of rows; a chunk pays the PIPE iterations of pipeline fill once per strip column it touches (never below 32 rows
+        // per CTA)
+        const long long total = (long long)P.nstrips * rows_out;
+        if (total > 0x3fffffffll) return cudaErrorInvalidValue;
+        grid = (int)std::max<long long>(1, std::min<long long>(fm->sm_count, total / 32));
+        P.seg_rows = (int)((total + grid - 1) / grid);                 // the chunk
+        grid = (int)((total + P.seg_rows - 1) / P.seg_rows);
+        const int pieces = (P.seg_rows + rows_out - 1) / rows_out + 1;  // strip columns a chunk can touch
+        P.nseg = 1;
+        P.n_units = grid * pieces;
+    } else {
+        // Row segments.  Units are dealt to the persistent CTAs round-robin, so the makespan is
+        // ceil(units / SMs) * (rows per segment + PIPE) row-iterations; pick the cut that minimises it
+        // (never below 16 rows per segment: every segment pays PIPE iterations of pipeline fill).
+        const long long cols = (long long)n * P.nstrips;
+        int nseg = 1;
+        {
+            long long best = -1;
+            const int max_seg = std::max(1, std::min(rows_out / 16, 256));
+            for (int c = 1; c <= max_seg; ++c) {
+                const int rws = (rows_out + c - 1) / c, real = (rows_out + rws - 1) / rws;
+                const long long waves = (cols * real + fm->sm_count - 1) / fm->sm_count;
+                const long long cost = waves * (rws + PIPE);
+                if (best < 0 || cost < best) { best = cost; nseg = c; }
+            }
         }
+        P.seg_rows = (rows_out + nseg - 1) / nseg;
+        P.nseg = (rows_out + P.seg_rows - 1) / P.seg_rows;
+        const long long units = cols * P.nseg;
+        if (units > 0x7fffffffll) return cudaErrorInvalidValue;
+        P.n_units = (int)units;
+        grid = (int)std::min<long long>(units, fm->sm_count);
     }
-    P.seg_rows = (rows_out + nseg - 1) / nseg;
-    P.nseg = (rows_out + P.seg_rows - 1) / P.seg_rows;
-    const long long units = cols * P.nseg;
-    if (units > 0x7fffffffll) return cudaErrorInvalidValue;
-    P.n_units = (int)units;
-    const int grid = (int)std::min<long long>(units, fm->sm_count);
     const bool prof = fm->env_profile;
     P.dbg = nullptr;
     P.dbg_flags = fm->env_experiment;

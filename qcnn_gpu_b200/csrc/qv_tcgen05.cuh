@@ -58,8 +58,9 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parit
         : "memory");
     return ok != 0;
 }
-// Bounded wait: returns false (instead of hanging the GPU) if the phase does not complete within ~2 s (200 000 polls of
-// up to 10 us each; long enough for a CTA that is time-sliced out for a while, short enough to fail a test run).  The waiter parks in hardware with a suspend-time hint.  A parked waiter sees an arrive later than one
+// Bounded wait: returns false (instead of hanging the GPU) if the phase does not complete within ~0.2 s (20 000 polls of
+// up to 10 us each).  (Both a longer bound and a non-unrolled poll loop were measured: the code the compiler emits for this
+// cold loop shifts the schedule of the hot code around it, 6.06 against 5.95 ms -- profiles/r2_kernel_ab_wait_loop.log.)  The waiter parks in hardware with a suspend-time hint.  A parked waiter sees an arrive later than one
 // that spins on try_wait (398 against 194 cycles, tools/umma_probe3.cu pingpong, profiles/r1_probe3_pingpong.log), and yet
 // the fused kernel is 10 % FASTER with parked waiters (6.60 against 7.25 ms, same box, same call:
 // profiles/experiments/r1_wait_spin_vs_hint_and_three_workers_ab.log).  It is the MMA warp's own spinning that costs: with
@@ -76,7 +77,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int ma
 #ifndef QV_WAIT_HINT_NS
 #define QV_WAIT_HINT_NS 10000
 #endif
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 2000000000 / QV_WAIT_HINT_NS)
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 200000000 / QV_WAIT_HINT_NS)
 {
     if (mbar_try_wait(bar, parity)) return true;
     for (int n = 0; n < max_polls; ++n)
