@@ -8,7 +8,11 @@ QP=32, 64 frames of 1920x1080 per GPU (weak scaling: every rank processes its ow
 frame-sharded, no data-path collective; the only collective is the int64 SSE all-reduce of the
 PSNR report, outside the timed region).  `value` = whole-job Mpixel/s with the frames already
 resident in HBM; `e2e` = the same metric through the host-buffer entry point
-qv_forward_frames_host (pinned host memory -> H2D -> net -> D2H every step).
+qv_forward_frames_host (pinned host memory -> H2D -> net -> D2H every step), with the box's measured
+concurrent copy ceiling beside it.  Further blocks of the same JSON line: `sustained` (320 back-to-back
+steps under the power cap, own clock sample), `config4` (BASELINE config 4: 240 x 4K frames sharded over the
+ranks) and `config5` (config 5: one 8K frame in N strips, halo rows read from the neighbour GPUs' memory),
+each with a bit-identity check against one GPU.
 
 --impl reference times the reference path's CPU restatement (oracle/, the only CPU implementation
 of this path that exists: the reference itself is cuDNN-only) on the box's host cores.

@@ -220,6 +220,7 @@ class QVRCNN:
     # -- one frame over several GPUs: strips with peer-mapped halo rows (qv_strip_*) -----------
     def strip_setup(self, img_height: int, row0: int, row1: int) -> None:
         _check(lib().qv_strip_setup(self._h, img_height, row0, row1))
+        self._strip_bytes = (row1 - row0) * self.width
 
     def strip_export(self) -> bytes:
         buf = C.create_string_buffer(STRIP_DESC_BYTES)
@@ -240,6 +241,7 @@ class QVRCNN:
 
     def strip_load(self, slot: int, rows_u8: np.ndarray, stream: int = 0) -> None:
         x = np.ascontiguousarray(rows_u8, np.uint8)
+        assert x.size == getattr(self, "_strip_bytes", -1), "strip_load: expected the %d bytes of this handle's rows, got %d" % (getattr(self, "_strip_bytes", -1), x.size)
         _check(lib().qv_strip_load(self._h, slot, x.ctypes.data, stream or None))
 
     def strip_forward(self, slot: int, d_out: int, stream: int = 0) -> None:
