@@ -110,6 +110,21 @@ def test_strips_equal_whole_frame_and_oracle(models, layout):
         n.strip_release()
 
 
+@pytest.mark.parametrize("h,w,S", [(18, 61, 3), (40, 130, 2), (97, 121, 5), (64, 8, 4)])
+def test_strips_ragged_geometries(models, h, w, S):
+    """Strips of exactly the halo height, heights that do not divide, widths below / just above one 120-pixel strip column:
+    every split reproduces the oracle's frame (strips on one device: the stream-ordered layout)."""
+    from oracle import oracle
+    image = formats.write_model_vect_c(models[37])
+    frames, _ = synth.make_frames(0xC0FFEE + 34, 2, h, w)
+    bounds = [shard.split(h, i, S)[0] for i in range(S)] + [h]
+    nets = _strip_nets(image, h, w, bounds, [0] * S)
+    got = _run_strips(nets, bounds, frames, w, [0] * S)
+    assert np.array_equal(got, oracle.OracleModel(image).forward_blu(frames))
+    for n in nets:
+        n.strip_release()
+
+
 def test_strip_api_refuses_what_it_cannot_do(models):
     image = formats.write_model_vect_c(models[27])
     h, w = 40, 64
