@@ -63,3 +63,21 @@ def test_fused_kernel_uses_tcgen05_and_parks_its_waiters(sass):
     allowed = {"UTCIMMA", "LDCU", "LDCU.64", "LDCU.128", "UMOV", "R2UR", "UIADD3", "UIMAD", "NOP", "R2UR.FILL", "MOV.SPILL"}
     assert set(body) <= allowed, set(body) - allowed
     assert len(body) <= 130, len(body)                                  # 27 MMAs + their table loads, little else
+
+
+def test_hot_kernel_is_the_build_that_was_measured(sass):
+    """The whole-frame kernel's speed depends on how the compiler lays its code out: with the SAME loops, a reordered
+    prologue ran 6.13 ms against 5.96, a non-unrolled (cold) wait loop 6.06 (profiles/r2_kernel_ab_wait_loop.log,
+    profiles/experiments/r2_bulk_copy_weights_ab.log).  profiles/r2_hot_kernel_sass.md5 is the instruction stream the
+    committed numbers were measured on; a different stream is not an error, but it is unmeasured -- warn loudly."""
+    import hashlib
+    import warnings
+    _, kernels = sass
+    hot = [k for k in kernels if "k_fusedILb1ELb0ELb0ELb0E" in k]
+    assert len(hot) == 1, hot
+    stream = "\n".join(re.sub(r"/\*[0-9a-f]+\*/", "", l) for l in kernels[hot[0]] if re.match(r"\s+/\*[0-9a-f]{4}\*/", l))
+    got = hashlib.md5((stream + "\n").encode()).hexdigest()
+    want = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_hot_kernel_sass.md5")).read().split()[0]
+    if got != want:
+        warnings.warn("k_fused<FAST, whole frames> was rebuilt into a different instruction stream (%s, measured: %s): "
+                      "re-run tools/kernel_ab.py before quoting its speed" % (got, want))
