@@ -76,13 +76,16 @@
 // shifts below put that many extra instructions (membar.cta, executed once) in front of the code of all roles / the workers and
 // C4 warps / the C4 warps.
 #ifndef QV_CODE_SHIFT
-#define QV_CODE_SHIFT 2
+#define QV_CODE_SHIFT 1          // best of the eight positions for this source (profiles/r2_kernel_ab_variants_by_alignment.log)
 #endif
 #ifndef QV_SHIFT_WORK
 #define QV_SHIFT_WORK 0
 #endif
 #ifndef QV_SHIFT_C4
 #define QV_SHIFT_C4 0
+#endif
+#ifndef QV_BULK_WEIGHTS
+#define QV_BULK_WEIGHTS 1        // the weight image goes global -> shared by cp.async.bulk (TMA engine); 0 = per-thread copy loop
 #endif
 #ifndef QV_LIGHT_PROF
 #define QV_LIGHT_PROF 0          // profiling build: 1 = only the timeline of block 0 (no per-MMA stamps, no per-thread counters)
@@ -346,6 +349,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
 #pragma unroll
     for (int j = 0; j < QV_CODE_SHIFT; ++j) asm volatile("membar.cta;" ::: "memory");
     // ---- one-time setup: weights -> smem, barriers, TMEM ---------------------------------
+#if QV_BULK_WEIGHTS
+    // the 122 KB weight image by four cp.async.bulk copies on the TMA engine while the threads clear the activation buffers:
+    // 2.5 us less per launch than a per-thread copy loop (profiles/experiments/r2_bulk_copy_weights_ab.log), which is 2 % of a
+    // single 1080p frame and 7 % of a tiny one; the batch time is the same (profiles/r2_kernel_ab_variants_by_alignment.log)
+    static_assert(WIMG_BYTES % 16 == 0 && WIMG_BYTES < (1 << 20), "cp.async.bulk size / mbarrier tx-count");
+    uint64_t *bar_in = reinterpret_cast<uint64_t *>(sm + OFF_CTRL + 40);
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(sm + OFF_CTRL + 56);
+    if (tid == 0) {
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
+        if (TMA) { mbar_init(&bar_in[0], 1); mbar_init(&bar_in[1], 1); }
+        mbar_init(bar_w, 1);
+        *s_fail = 0;
+        mbar_fence_init();
+        constexpr uint32_t PART = (WIMG_BYTES / 4 + 15) / 16 * 16;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_w)), "r"((uint32_t)WIMG_BYTES) : "memory");
+#pragma unroll
+        for (uint32_t o = 0; o < (uint32_t)WIMG_BYTES; o += PART) {
+            const uint32_t n = o + PART <= (uint32_t)WIMG_BYTES ? PART : (uint32_t)WIMG_BYTES - o;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sm + o)), "l"(P.wimg + o), "r"(n), "r"(smem_u32(bar_w)) : "memory");
+        }
+    }
+    for (int i = tid; i < (OFF_CTRL - OFF_A1) / 16; i += NTHREADS)
+        reinterpret_cast<uint4 *>(sm + OFF_A1)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0 && !tc::mbar_wait(bar_w, 0)) *s_fail = 1;
+#else
     for (int i = tid; i < WIMG_BYTES / 16; i += NTHREADS)
         reinterpret_cast<uint4 *>(sm)[i] = reinterpret_cast<const uint4 *>(P.wimg)[i];
     for (int i = tid; i < (OFF_CTRL - OFF_A1) / 16; i += NTHREADS)      // finite data everywhere the MMAs may read
@@ -358,6 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         *s_fail = 0;
         mbar_fence_init();
     }
+#endif
     if (warp == 8) { tmem_alloc(s_tmem, TM_COLS); tmem_relinquish(); }
     fence_proxy_async_smem();
     fence_before_sync();

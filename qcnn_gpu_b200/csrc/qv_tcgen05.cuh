@@ -80,6 +80,9 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int ma
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_polls = 200000000 / QV_WAIT_HINT_NS)
 {
     if (mbar_try_wait(bar, parity)) return true;
+#ifdef QV_WAIT_UNROLL1
+#pragma unroll 1
+#endif
     for (int n = 0; n < max_polls; ++n)
         if (mbar_try_wait_hint(bar, parity, (uint32_t)QV_WAIT_HINT_NS)) return true;
     return false;
