@@ -76,7 +76,7 @@
 // shifts below put that many extra instructions (membar.cta, executed once) in front of the code of all roles / the workers and
 // C4 warps / the C4 warps.
 #ifndef QV_CODE_SHIFT
-#define QV_CODE_SHIFT 1          // best of the eight positions for this source (profiles/r2_kernel_ab_variants_by_alignment.log)
+#define QV_CODE_SHIFT 7          // best of the eight positions for this source (profiles/r2_kernel_ab_one_worker_per_quarter.log)
 #endif
 #ifndef QV_SHIFT_WORK
 #define QV_SHIFT_WORK 0
@@ -131,7 +131,11 @@ constexpr int OFF_IN_T = (SMEM_BYTES + 127) / 128 * 128;
 constexpr int SMEM_BYTES_T = OFF_IN_T + IN_SLOTS * IN_PITCH_T;
 static_assert(SMEM_BYTES_T <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 
-constexpr int NWORKER = 256, NC4 = 128, NTHREADS = NWORKER + 32 + NC4;   // warps 0-7 workers, 8 MMA issue, 9-12 C4
+#ifndef QV_ONE_WORKER
+#define QV_ONE_WORKER 1          // one worker warp per TMEM lane quarter (ten accumulator groups each); 0 = two (five each), the round-1 arrangement
+#endif
+constexpr int NWORKER = QV_ONE_WORKER ? 128 : 256, NC4 = 128, NTHREADS = NWORKER + 32 + NC4;   // warps 0-7 workers, 8 MMA issue, 9-12 C4
+constexpr int MMA_WARP = NWORKER / 32;
 constexpr int TR_ITER0 = 300, TR_N = 8;    // profile-mode timeline window
 constexpr int PIPE = 14;                   // pipeline depth in rows: output row y0 appears at iteration 14
 
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         mbar_fence_init();
     }
 #endif
-    if (warp == 8) { tmem_alloc(s_tmem, TM_COLS); tmem_relinquish(); }
+    if (warp == MMA_WARP) { tmem_alloc(s_tmem, TM_COLS); tmem_relinquish(); }
     fence_proxy_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     const uint32_t tm = *s_tmem;
     const uint32_t sbase = smem_u32(sm);
 
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         // =============================== MMA issuer ========================================
         // The whole warp runs the control flow (so that descriptors stay in uniform registers);
         // one elected lane issues the tcgen05 instructions.
@@ -534,7 +538,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                     uint8_t *dst1 = sm + OFF_A1 + wrap_sub(c3, 1, 3) * A1_ROW + (4 + m) * 16;
                     const uint32_t d1 = tm_lane + TM_D1 + par * 64;
                     uint32_t ra[16], rb[16], rc[16], rd[16], re[16];
-                    if (hh == 0) {
+                    // the two halves of a quarter's ten accumulator groups (with two worker warps per quarter: one half each)
+                    auto drain_a = [&]() {
                         const bool v2 = row_ok(R1 - 5) && xa2, v2n = row_ok(R1 - 4) && xa2, v3 = row_ok(R1 - 8) && xa3;
                         uint8_t *dst2 = sm + OFF_A2 + wrap_sub(c3, 5, 3) * A2_ROW + (6 + m) * 16;
                         uint8_t *dst2n = sm + OFF_A2 + wrap_sub(c3, 4, 3) * A2_ROW + (6 + m) * 16;
@@ -548,7 +553,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                         requant_store<FAST, 64>(rc, P, P.q22, v2, dst2 + 2 * PLANE);
                         requant_store<FAST, 80>(rd, P, P.q21, v2n, dst2n + 0 * PLANE);
                         if (!(EXP & 1)) requant_store<FAST, 112>(re, P, P.q31, v3, sm + OFF_A3 + wrap_sub(c3, 8, 3) * A2_ROW + (7 + m) * 16);   // a3 row R1-8 plane 0
-                    } else {
+                    };
+                    auto drain_b = [&]() {
                         const bool v2n = row_ok(R1 - 4) && xa2, v3n = row_ok(R1 - 7) && xa3;
                         uint8_t *dst2n = sm + OFF_A2 + wrap_sub(c3, 4, 3) * A2_ROW + (6 + m) * 16;
                         const uint32_t d32 = tm_lane + TM_D32 + par * 32;
@@ -564,7 +570,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
                             requant_store<FAST, 128>(rd, P, P.q32, v3n, dst3n + 1 * PLANE);
                             requant_store<FAST, 144>(re, P, P.q32, v3n, dst3n + 2 * PLANE);
                         }
+                    };
+#if QV_ONE_WORKER
+                    if (FAST) {
+                        // one warp per quarter: all ten loads in flight, one wait, then the arithmetic
+                        uint32_t rf[16], rg[16], rh[16], ri[16], rj[16];
+                        const bool v2 = row_ok(R1 - 5) && xa2, v2n = row_ok(R1 - 4) && xa2, v3 = row_ok(R1 - 8) && xa3, v3n = row_ok(R1 - 7) && xa3;
+                        uint8_t *dst2 = sm + OFF_A2 + wrap_sub(c3, 5, 3) * A2_ROW + (6 + m) * 16;
+                        uint8_t *dst2n = sm + OFF_A2 + wrap_sub(c3, 4, 3) * A2_ROW + (6 + m) * 16;
+                        uint8_t *dst3n = sm + OFF_A3 + wrap_sub(c3, 7, 3) * A2_ROW + (7 + m) * 16;
+                        const uint32_t d32 = tm_lane + TM_D32 + par * 32;
+                        tmem_ld_x16(d1 + 0, ra); tmem_ld_x16(d1 + 16, rb); tmem_ld_x16(d1 + 32, rf); tmem_ld_x16(d1 + 48, rg);
+                        tmem_ld_x16(tm_lane + TM_R22 + wrap_sub(c6, 5, 6) * 16, rc);
+                        tmem_ld_x16(tm_lane + TM_R21 + ((R1p - 4) & 3) * 32, rd);
+                        tmem_ld_x16(tm_lane + TM_R21 + ((R1p - 4) & 3) * 32 + 16, rh);
+                        tmem_ld_x16(tm_lane + TM_R31 + ((R1p - 8) & 3) * 16, re);
+                        tmem_ld_x16(d32 + 0, ri); tmem_ld_x16(d32 + 16, rj);
+                        tmem_ld_wait();
+                        requant_store<FAST, 0>(ra, P, P.q1, v1, dst1 + 0 * PLANE);
+                        requant_store<FAST, 16>(rb, P, P.q1, v1, dst1 + 1 * PLANE);
+                        requant_store<FAST, 32>(rf, P, P.q1, v1, dst1 + 2 * PLANE);
+                        requant_store<FAST, 48>(rg, P, P.q1, v1, dst1 + 3 * PLANE);
+                        requant_store<FAST, 64>(rc, P, P.q22, v2, dst2 + 2 * PLANE);
+                        requant_store<FAST, 80>(rd, P, P.q21, v2n, dst2n + 0 * PLANE);
+                        requant_store<FAST, 96>(rh, P, P.q21, v2n, dst2n + 1 * PLANE);
+                        requant_store<FAST, 112>(re, P, P.q31, v3, sm + OFF_A3 + wrap_sub(c3, 8, 3) * A2_ROW + (7 + m) * 16);
+                        requant_store<FAST, 128>(ri, P, P.q32, v3n, dst3n + 1 * PLANE);
+                        requant_store<FAST, 144>(rj, P, P.q32, v3n, dst3n + 2 * PLANE);
+                    } else {
+                        drain_a();                                  // the reference-formula requantiser needs more registers: two rounds
+                        drain_b();
                     }
+#else
+                    if (hh == 0) drain_a(); else drain_b();
+#endif
                 }
                 lap(1);
                 if (i + 1 < niter) {
@@ -748,7 +787,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tm, TM_COLS);
+    if (warp == MMA_WARP) tmem_dealloc(tm, TM_COLS);
     if (tid == 0 && *s_fail) {
         *reinterpret_cast<volatile int *>(P.fail_flag) = *s_fail;
         __threadfence_system();
