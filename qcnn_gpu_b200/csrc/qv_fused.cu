@@ -520,8 +520,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             for (int i = 0; i < niter; ++i, c3 = wrap_inc(c3, 3), c6 = wrap_inc(c6, 6)) {
                 const int R1 = y0 - 4 + i, R1p = R1 + 4096;
                 if (PROF)
-                    tr_slot = (P.dbg && unit == 0 && (tid == 0 || tid == 128) && i >= TR_ITER0 && i < TR_ITER0 + TR_N)
-                                  ? (i - TR_ITER0) * 16 + 2 + (tid >> 7) * 4 : -1;
+                    tr_slot = (P.dbg && unit == 0 && (tid == 0 || tid == NWORKER / 2) && i >= TR_ITER0 && i < TR_ITER0 + TR_N)
+                                  ? (i - TR_ITER0) * 16 + 2 + (tid / (NWORKER / 2)) * 4 : -1;
                 if (PROF && i >= 1 && (P.dbg_flags & 2)) {           // experiment: wait, but drain nothing
                     warp_wait(&bar_mma[ev_mma & 1], (ev_mma >> 1) & 1, lane, s_fail);
                     ++ev_mma;
@@ -624,10 +624,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
             tr_slot = -1;
             lap(5);
         }
-        if (PROF && P.dbg && (tid == 0 || tid == 128))
+        if (PROF && P.dbg && (tid == 0 || tid == NWORKER / 2))
         {
-            for (int k = 0; k < 6; ++k) P.dbg[blockIdx.x * 16 + 2 + (tid >> 7) * 6 + k] = tw[k];
-            P.dbg[blockIdx.x * 16 + 14 + (tid >> 7)] = t_ldtm;
+            for (int k = 0; k < 6; ++k) P.dbg[blockIdx.x * 16 + 2 + (tid / (NWORKER / 2)) * 6 + k] = tw[k];
+            P.dbg[blockIdx.x * 16 + 14 + (tid / (NWORKER / 2))] = t_ldtm;
         }
     } else {
         // ================================= C4 warps ==========================================
@@ -1250,7 +1250,7 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
         const double iters = (double)P.n_units / grid * (P.seg_rows + PIPE);
         fprintf(stderr, "[qv fused profile] units=%d grid=%d iters/block~%.0f | cycles per iteration: MMA warp wait=%.0f issue=%.0f | "
                 "worker w0: wait_mma=%.0f drain=%.0f (of which tcgen05.ld+wait %.0f) fence+arrive=%.0f bar=%.0f | "
-                "worker w4: wait_mma=%.0f drain=%.0f (tcgen05.ld+wait %.0f) fence+arrive=%.0f bar=%.0f\n",
+                "second traced worker (thread NWORKER/2): wait_mma=%.0f drain=%.0f (tcgen05.ld+wait %.0f) fence+arrive=%.0f bar=%.0f\n",
                 P.n_units, grid, iters, a[0] / iters, a[1] / iters, a[2] / iters, a[3] / iters, a[14] / iters, a[4] / iters, a[5] / iters,
                 a[8] / iters, a[9] / iters, a[15] / iters, a[10] / iters, a[11] / iters);
         // timeline of block 0: per traced iteration, cycles relative to the first issue start
