@@ -221,6 +221,40 @@ def test_two_threads_load_and_run_two_handles_concurrently(models):
             assert np.array_equal(got[(qp, rep)], want), (qp, rep)
 
 
+def test_random_geometries_fused_equals_layered_and_oracle(models):
+    """Seeded sweep over ragged geometries: 48 random (frames, height, width, QP) -- widths around the 120-pixel strip columns,
+    heights around the row-segment cuts -- fused == layered bit for bit, the small ones also == oracle; and for each a random
+    row window through qv_forward_rows_device (the row-window instantiation of the fused kernel) == the same rows of the
+    whole-frame result."""
+    import torch
+    rng = np.random.default_rng(20261018)
+    net_cache = {}
+    for case in range(48):
+        qp = int(rng.choice([22, 27, 32, 37]))
+        n = int(rng.integers(1, 4))
+        h = int(rng.choice([rng.integers(1, 40), rng.integers(40, 300)]))
+        w = int(rng.choice([rng.integers(1, 130), 120 * rng.integers(1, 4) + rng.integers(-3, 4), rng.integers(130, 500)]))
+        w = max(w, 1)
+        x = synth.make_uniform_frames(1000 + case, n, h, w) if case % 3 == 0 else synth.make_frames(2000 + case, n, h, w)[0]
+        net = api.QVRCNN(0, n, 1, h, w)
+        net.load_static_para_mem(formats.write_model_vect_c(models[qp]))
+        net.set_impl(api.IMPL_LAYERED)
+        out_l = net.forward_frames_host(x)
+        net.set_impl(api.IMPL_FUSED)
+        out_f = net.forward_frames_host(x)
+        assert np.array_equal(out_l, out_f), (case, qp, n, h, w, int((out_l != out_f).sum()))
+        if n * h * w <= 40000:
+            assert np.array_equal(out_f, _oracle(models[qp]).forward_blu(x)), (case, qp, n, h, w)
+        # a random output window [y0, y1) with the rows it needs
+        y0 = int(rng.integers(0, h)); y1 = int(rng.integers(y0 + 1, h + 1))
+        r0, r1 = max(0, y0 - 6), min(h, y1 + 6)
+        d_in = torch.from_numpy(np.ascontiguousarray(x[0, r0:r1])).cuda()
+        d_out = torch.zeros((y1 - y0, w), dtype=torch.uint8, device="cuda")
+        net.forward_rows_device(d_in.data_ptr(), h, r0, r1 - r0, d_out.data_ptr(), y0, y1)
+        assert np.array_equal(d_out.cpu().numpy(), out_f[0, y0:y1]), (case, "window", h, w, y0, y1)
+        net.close()
+
+
 def test_full_size_properties_4k_and_8k(models):
     """BASELINE configs 4 and 5 at their real frame sizes, through properties that need no CPU oracle run:
     (a) 3840x2160, QP 27: frames are independent -- a frame inside a batch of 3 equals the same frame processed alone,
