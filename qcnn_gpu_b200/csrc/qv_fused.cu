@@ -76,7 +76,7 @@
 // shifts below put that many extra instructions (membar.cta, executed once) in front of the code of all roles / the workers and
 // C4 warps / the C4 warps.
 #ifndef QV_CODE_SHIFT
-#define QV_CODE_SHIFT 7          // best of the eight positions for this source (profiles/r2_kernel_ab_one_worker_per_quarter.log)
+#define QV_CODE_SHIFT 3          // best of the eight positions for this source (profiles/r2_kernel_ab_row_line_decomposition.log)
 #endif
 #ifndef QV_SHIFT_WORK
 #define QV_SHIFT_WORK 0
@@ -161,7 +161,7 @@ struct alignas(64) FusedParams {
     const uint8_t *in;
     uint8_t *out;
     const uint8_t *wimg;
-    int n_frames, H, W, nstrips, nseg, seg_rows, n_units;
+    int n_frames, H, W, nstrips, nseg, seg_rows, n_units, linear;
     // Spatial partition of one frame over several GPUs (qv_strip_*): this launch produces image rows [ys, ye); `in` holds
     // rows [own0, own1); rows [rlo, own0) are read through in_top and rows [own1, rhi) through in_bot -- virtual bases too,
     // pointing into the NEIGHBOUR GPUs' memory (peer-mapped over NVLink), valid once *flag_top / *flag_bot have reached
@@ -242,7 +242,16 @@ template <bool ROWS>
 __device__ __forceinline__ UnitGeo unit_geo(const FusedParams &P, int unit, int H)
 {
     UnitGeo g;
-    if (!ROWS) {                       // whole frames: (frame, strip column, equal row segment)
+    if (!ROWS && P.linear) {           // whole frames, dealt out by rows: the line runs over all (frame, strip) columns
+        const int b = unit % (int)gridDim.x, j = unit / (int)gridDim.x;
+        const int lo = b * P.seg_rows, hi = min(P.n_frames * P.nstrips * H, lo + P.seg_rows), c = lo / H + j;
+        const int start = j == 0 ? lo : c * H, end = min(hi, (c + 1) * H);
+        g.f = c / P.nstrips;
+        g.strip = c - g.f * P.nstrips;
+        g.y0 = start - c * H;
+        g.y1 = g.y0 + (end - start);
+        g.ok = start < end;
+    } else if (!ROWS) {                // whole frames: (frame, strip column, equal row segment)
         const int seg = unit % P.nseg;
         g.strip = (unit / P.nseg) % P.nstrips;
         g.f = unit / (P.nseg * P.nstrips);
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         const uint32_t r22 = tm + TM_R22, r21 = tm + TM_R21, r31 = tm + TM_R31;
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const UnitGeo g = unit_geo<ROWS>(P, unit, H);
-            if (ROWS && !g.ok) continue;
+            if (!g.ok) continue;
             const int y0 = g.y0, y1 = g.y1;
             const int niter = y1 - y0 + PIPE;
             int ph = mod_pos(y0 - 4, N_PHASE);
@@ -506,7 +515,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };      // workers + C4 warps
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const UnitGeo g = unit_geo<ROWS>(P, unit, H);
-            if (ROWS && !g.ok) continue;
+            if (!g.ok) continue;
             const int strip = g.strip, f = g.f, y0 = g.y0, y1 = g.y1;
             const int X0 = strip * WT;
             const int niter = y1 - y0 + PIPE;
@@ -644,7 +653,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
             const UnitGeo g = unit_geo<ROWS>(P, unit, H);
-            if (ROWS && !g.ok) continue;
+            if (!g.ok) continue;
             const int strip = g.strip, f = g.f, y0 = g.y0, y1 = g.y1;
             const int X0 = strip * WT;
             const int niter = y1 - y0 + PIPE;
@@ -900,7 +909,7 @@ struct FusedModel {
     bool fast = true;
     int sm_count = 148;
     // environment switches, read once at upload (never on the per-launch path)
-    bool env_profile = false, env_test_fail = false, env_tma = false;
+    bool env_profile = false, env_test_fail = false, env_tma = false, env_linear = true;
     int env_experiment = 0;
     void *encode_tiled = nullptr;      // cuTensorMapEncodeTiled (driver entry point; the library does not link libcuda)
 };
@@ -1100,6 +1109,7 @@ FusedModel *fused_upload(const ModelHost &m, cudaStream_t st)
     fm->env_experiment = getenv("QV_FUSED_EXPERIMENT") ? atoi(getenv("QV_FUSED_EXPERIMENT")) : 0;
     fm->env_test_fail = getenv("QV_FUSED_TEST_FAIL") != nullptr;     // tests only: make every CTA report a base mismatch
     fm->env_tma = getenv("QV_FUSED_TMA") != nullptr && atoi(getenv("QV_FUSED_TMA")) != 0;
+    fm->env_linear = !(getenv("QV_FUSED_LINEAR") && atoi(getenv("QV_FUSED_LINEAR")) == 0);      // A/B switch: 0 = equal row segments only
     if (fm->env_tma) {
         cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fm->encode_tiled, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
@@ -1212,6 +1222,18 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
         if (units > 0x7fffffffll) return cudaErrorInvalidValue;
         P.n_units = (int)units;
         grid = (int)std::min<long long>(units, fm->sm_count);
+        // ... or the line of cols * H row-iterations cut into one equal chunk per SM (see unit_geo): no idle SMs in the last
+        // wave, one pipeline fill per strip column a chunk touches.  64 x 1080p: 7585 iterations per SM against 7658.
+        const long long total = cols * rows_out, g2 = std::max<long long>(1, std::min<long long>(fm->sm_count, total / 32));
+        const long long chunk = (total + g2 - 1) / g2, pieces = (chunk + rows_out - 1) / rows_out + 1;
+        const long long cost_equal = (units + grid - 1) / grid * (P.seg_rows + PIPE);
+        if (fm->env_linear && total <= 0x3fffffffll && chunk + pieces * PIPE < cost_equal) {
+            P.linear = 1;
+            P.seg_rows = (int)chunk;
+            grid = (int)((total + chunk - 1) / chunk);
+            P.nseg = 1;
+            P.n_units = grid * (int)pieces;
+        }
     }
     const bool prof = fm->env_profile;
     P.dbg = nullptr;
@@ -1247,7 +1269,7 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
         cudaFree(P.dbg);
         double a[16] = {0};
         for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
-        const double iters = (double)P.n_units / grid * (P.seg_rows + PIPE);
+        const double iters = P.linear ? (double)P.seg_rows + PIPE * (P.n_units / grid - 1) : (double)P.n_units / grid * (P.seg_rows + PIPE);
         fprintf(stderr, "[qv fused profile] units=%d grid=%d iters/block~%.0f | cycles per iteration: MMA warp wait=%.0f issue=%.0f | "
                 "worker w0: wait_mma=%.0f drain=%.0f (of which tcgen05.ld+wait %.0f) fence+arrive=%.0f bar=%.0f | "
                 "second traced worker (thread NWORKER/2): wait_mma=%.0f drain=%.0f (tcgen05.ld+wait %.0f) fence+arrive=%.0f bar=%.0f\n",
