@@ -76,7 +76,7 @@
 // shifts below put that many extra instructions (membar.cta, executed once) in front of the code of all roles / the workers and
 // C4 warps / the C4 warps.
 #ifndef QV_CODE_SHIFT
-#define QV_CODE_SHIFT 3          // best of the eight positions for this source (profiles/r2_kernel_ab_row_line_decomposition.log)
+#define QV_CODE_SHIFT 5          // best of the eight positions for this source (profiles/r2_kernel_ab_row_line_decomposition.log)
 #endif
 #ifndef QV_SHIFT_WORK
 #define QV_SHIFT_WORK 0
@@ -161,7 +161,7 @@ struct alignas(64) FusedParams {
     const uint8_t *in;
     uint8_t *out;
     const uint8_t *wimg;
-    int n_frames, H, W, nstrips, nseg, seg_rows, n_units, linear;
+    int n_frames, H, W, nstrips, nseg, seg_rows, n_units, linear, perm_q, perm_s0, perm_r;
     // Spatial partition of one frame over several GPUs (qv_strip_*): this launch produces image rows [ys, ye); `in` holds
     // rows [own0, own1); rows [rlo, own0) are read through in_top and rows [own1, rhi) through in_bot -- virtual bases too,
     // pointing into the NEIGHBOUR GPUs' memory (peer-mapped over NVLink), valid once *flag_top / *flag_bot have reached
@@ -246,8 +246,14 @@ __device__ __forceinline__ UnitGeo unit_geo(const FusedParams &P, int unit, int 
         const int b = unit % (int)gridDim.x, j = unit / (int)gridDim.x;
         const int lo = b * P.seg_rows, hi = min(P.n_frames * P.nstrips * H, lo + P.seg_rows), c = lo / H + j;
         const int start = j == 0 ? lo : c * H, end = min(hi, (c + 1) * H);
-        g.f = c / P.nstrips;
-        g.strip = c - g.f * P.nstrips;
+        // position c on the line -> column q + s * perm_q: CTAs b and b + 1 are ~perm_s positions apart, so they work on
+        // neighbouring strip columns of one frame at the same time and the shared halo columns and output sectors meet in L2
+        const int full = P.perm_r * (P.perm_s0 + 1);
+        const int q = c < full ? c / (P.perm_s0 + 1) : P.perm_r + (c - full) / P.perm_s0;
+        const int sl = c < full ? c - q * (P.perm_s0 + 1) : (c - full) - (q - P.perm_r) * P.perm_s0;
+        const int col = q + sl * P.perm_q;
+        g.f = col / P.nstrips;
+        g.strip = col - g.f * P.nstrips;
         g.y0 = start - c * H;
         g.y1 = g.y0 + (end - start);
         g.ok = start < end;
@@ -1233,6 +1239,10 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
             grid = (int)((total + chunk - 1) / chunk);
             P.nseg = 1;
             P.n_units = grid * (int)pieces;
+            const long long per = (cols + grid - 1) / grid;               // columns per chunk, rounded up
+            P.perm_q = (int)((cols + per - 1) / per);
+            P.perm_s0 = (int)(cols / P.perm_q);
+            P.perm_r = (int)(cols % P.perm_q);
         }
     }
     const bool prof = fm->env_profile;
