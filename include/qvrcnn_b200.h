@@ -198,6 +198,15 @@ QV_API int qv_get_activation(qv_net *net, int which /*1,2,3*/, int8_t *host_out)
    is null or too small is not written.  tests/test_fused_tables.py emulates the kernel's dataflow on these. */
 QV_API int qv_debug_fused_tables(const void *model_image, size_t len, uint8_t *wimg, uint32_t *ops, int32_t *consts, size_t sizes[3]);
 
+/* Test hook, needs no GPU: how the fused kernel's launch for n_frames frames of height x width (output rows [row0, row1);
+   row_window != 0: a row-window launch of one frame, as the strip entry points issue) is dealt out to sm_count persistent
+   CTAs -- the host's plan (equal row segments, or one equal chunk of the row line per SM when allow_line != 0 and that is
+   cheaper) read back through the same unit_geo() the kernel uses.  units: 5 ints per work unit (cta, frame, strip column, y0, y1);
+   *n_units = capacity in units on entry, count on return (a null or too small buffer is not written).
+   tests/test_fused_units.py checks that every (frame, column, row) is covered exactly once and the load is balanced. */
+QV_API int qv_debug_fused_units(int sm_count, int n_frames, int height, int width, int row0, int row1, int row_window, int allow_line,
+                                int32_t *units, size_t *n_units, int *grid);
+
 /* ---- model-file converters ------------------------------------------------- */
 /* model_qfp_HWCN2NCHW_VECT_C   inference/qvrcnn.cu:558-585 */
 QV_API int qv_convert_model_hwcn_to_vect_c(const char *file_in, const char *file_out);

@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "qv_set_impl", "qv_get_impl", "qv_launch_count", "qv_get_activation",
     "qv_convert_model_hwcn_to_vect_c", "qv_yuv_read_luma", "qv_yuv_read_frame", "qv_yuv_write_recon",
     "qv_psnr", "qv_psnr_from_sse", "qv_solve_quant_params", "qv_write_quant_params_cpp", "qv_quantize_layer",
-    "qv_debug_fused_tables", "qv_synchronize",
+    "qv_debug_fused_tables", "qv_debug_fused_units", "qv_synchronize",
     "qv_strip_setup", "qv_strip_export", "qv_strip_attach", "qv_strip_input", "qv_strip_acquire", "qv_strip_load",
     "qv_strip_forward", "qv_strip_release",
 )

@@ -325,6 +325,22 @@ int qv_debug_fused_tables(const void *image, size_t len, uint8_t *wimg, uint32_t
     return QV_OK;
 }
 
+int qv_debug_fused_units(int sm_count, int n_frames, int height, int width, int row0, int row1, int row_window, int allow_line,
+                         int32_t *units, size_t *n_units, int *grid)
+{
+    if (!n_units || !grid) { set_error("qv_debug_fused_units: null argument"); return QV_ERR_ARG; }
+    std::vector<int> u;
+    int g = 0;
+    if (fused_debug_units(sm_count, n_frames, height, width, row0, row1, row_window != 0, allow_line != 0, u, g)) {
+        set_error("qv_debug_fused_units: bad geometry");
+        return QV_ERR_ARG;
+    }
+    if (units && *n_units >= u.size() / 5) memcpy(units, u.data(), u.size() * sizeof(int));
+    *n_units = u.size() / 5;
+    *grid = g;
+    return QV_OK;
+}
+
 int qv_load_static_para(qv_net *net, const char *filename)
 {
     if (!net) { set_error("qv_load_static_para: null handle"); return QV_ERR_ARG; }

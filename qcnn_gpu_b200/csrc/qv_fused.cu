@@ -239,11 +239,11 @@ __device__ __forceinline__ bool peer_wait(const uint32_t *flag, uint32_t seq)
 // ok = false for a piece that does not exist.
 struct UnitGeo { int strip, f, y0, y1; bool ok; };
 template <bool ROWS>
-__device__ __forceinline__ UnitGeo unit_geo(const FusedParams &P, int unit, int H)
+__host__ __device__ __forceinline__ UnitGeo unit_geo(const FusedParams &P, int unit, int H, int grid)
 {
     UnitGeo g;
     if (!ROWS && P.linear) {           // whole frames, dealt out by rows: the line runs over all (frame, strip) columns
-        const int b = unit % (int)gridDim.x, j = unit / (int)gridDim.x;
+        const int b = unit % grid, j = unit / grid;
         const int lo = b * P.seg_rows, hi = min(P.n_frames * P.nstrips * H, lo + P.seg_rows), c = lo / H + j;
         const int start = j == 0 ? lo : c * H, end = min(hi, (c + 1) * H);
         // position c on the line -> column q + s * perm_q: CTAs b and b + 1 are ~perm_s positions apart, so they work on
@@ -265,7 +265,7 @@ __device__ __forceinline__ UnitGeo unit_geo(const FusedParams &P, int unit, int 
         g.y1 = min(H, g.y0 + P.seg_rows);
         g.ok = true;
     } else {
-        const int R = P.ye - P.ys, b = unit % (int)gridDim.x, j = unit / (int)gridDim.x;
+        const int R = P.ye - P.ys, b = unit % grid, j = unit / grid;
         const int lo = b * P.seg_rows, hi = min(P.nstrips * R, lo + P.seg_rows), c0 = lo / R;
         const int start = j == 0 ? lo : (c0 + j) * R, end = min(hi, (c0 + j + 1) * R);
         g.strip = c0 + j;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         if ((sbase >> 4) != P.sbase16 || tm != P.tmem_base) { if (lane == 0) *s_fail = 2; }     // c_ops does not describe this CTA
         const uint32_t r22 = tm + TM_R22, r21 = tm + TM_R21, r31 = tm + TM_R31;
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-            const UnitGeo g = unit_geo<ROWS>(P, unit, H);
+            const UnitGeo g = unit_geo<ROWS>(P, unit, H, (int)gridDim.x);
             if (!g.ok) continue;
             const int y0 = g.y0, y1 = g.y1;
             const int niter = y1 - y0 + PIPE;
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         };
         auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };      // workers + C4 warps
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-            const UnitGeo g = unit_geo<ROWS>(P, unit, H);
+            const UnitGeo g = unit_geo<ROWS>(P, unit, H, (int)gridDim.x);
             if (!g.ok) continue;
             const int strip = g.strip, f = g.f, y0 = g.y0, y1 = g.y1;
             const int X0 = strip * WT;
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(const __grid_constant__ F
         uint32_t ev_work = 0, tma_n = 0;
         auto worker_bar = []() { asm volatile("bar.sync 1, %0;" ::"n"(NWORKER + NC4) : "memory"); };
         for (int unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-            const UnitGeo g = unit_geo<ROWS>(P, unit, H);
+            const UnitGeo g = unit_geo<ROWS>(P, unit, H, (int)gridDim.x);
             if (!g.ok) continue;
             const int strip = g.strip, f = g.f, y0 = g.y0, y1 = g.y1;
             const int X0 = strip * WT;
@@ -1161,6 +1161,85 @@ int fused_take_failure(const FusedModel *fm)
     return f;
 }
 
+// How a launch is dealt out to the persistent CTAs: fills the geometry fields of P (nstrips, nseg, seg_rows, n_units, linear,
+// perm_*) from n_frames, W and the output rows [ys, ye), and returns the grid.  Host-only arithmetic; unit_geo() is its reader.
+static cudaError_t plan_units(FusedParams &P, int sm_count, bool allow_linear, bool rows_mode, int &grid)
+{
+    const int rows_out = P.ye - P.ys;
+    P.nstrips = (P.W + WT - 1) / WT;
+    grid = 1;
+    P.linear = 0;
+    if (rows_mode) {
+        // one line of nstrips * rows_out row-iterations, cut into equal chunks (rows_unit): every SM gets the same number
+        // of rows; a chunk pays the PIPE iterations of pipeline fill once per strip column it touches (never below 32 rows
+        // per CTA)
+        const long long total = (long long)P.nstrips * rows_out;
+        if (total > 0x3fffffffll) return cudaErrorInvalidValue;
+        grid = (int)std::max<long long>(1, std::min<long long>(sm_count, total / 32));
+        P.seg_rows = (int)((total + grid - 1) / grid);                 // the chunk
+        grid = (int)((total + P.seg_rows - 1) / P.seg_rows);
+        const int pieces = (P.seg_rows + rows_out - 1) / rows_out + 1;  // strip columns a chunk can touch
+        P.nseg = 1;
+        P.n_units = grid * pieces;
+    } else {
+        // Row segments.  Units are dealt to the persistent CTAs round-robin, so the makespan is
+        // ceil(units / SMs) * (rows per segment + PIPE) row-iterations; pick the cut that minimises it
+        // (never below 16 rows per segment: every segment pays PIPE iterations of pipeline fill).
+        const long long cols = (long long)P.n_frames * P.nstrips;
+        int nseg = 1;
+        {
+            long long best = -1;
+            const int max_seg = std::max(1, std::min(rows_out / 16, 256));
+            for (int c = 1; c <= max_seg; ++c) {
+                const int rws = (rows_out + c - 1) / c, real = (rows_out + rws - 1) / rws;
+                const long long waves = (cols * real + sm_count - 1) / sm_count;
+                const long long cost = waves * (rws + PIPE);
+                if (best < 0 || cost < best) { best = cost; nseg = c; }
+            }
+        }
+        P.seg_rows = (rows_out + nseg - 1) / nseg;
+        P.nseg = (rows_out + P.seg_rows - 1) / P.seg_rows;
+        const long long units = cols * P.nseg;
+        if (units > 0x7fffffffll) return cudaErrorInvalidValue;
+        P.n_units = (int)units;
+        grid = (int)std::min<long long>(units, sm_count);
+        // ... or the line of cols * H row-iterations cut into one equal chunk per SM (see unit_geo): no idle SMs in the last
+        // wave, one pipeline fill per strip column a chunk touches.  64 x 1080p: 7585 iterations per SM against 7658.
+        const long long total = cols * rows_out, g2 = std::max<long long>(1, std::min<long long>(sm_count, total / 32));
+        const long long chunk = (total + g2 - 1) / g2, pieces = (chunk + rows_out - 1) / rows_out + 1;
+        const long long cost_equal = (units + grid - 1) / grid * (P.seg_rows + PIPE);
+        if (allow_linear && total <= 0x3fffffffll && chunk + pieces * PIPE < cost_equal) {
+            P.linear = 1;
+            P.seg_rows = (int)chunk;
+            grid = (int)((total + chunk - 1) / chunk);
+            P.nseg = 1;
+            P.n_units = grid * (int)pieces;
+            const long long per = (cols + grid - 1) / grid;               // columns per chunk, rounded up
+            P.perm_q = (int)((cols + per - 1) / per);
+            P.perm_s0 = (int)(cols / P.perm_q);
+            P.perm_r = (int)(cols % P.perm_q);
+        }
+    }
+    return cudaSuccess;
+}
+
+// Test hook (qv_debug_fused_units): the units of a launch as the kernel's CTAs will see them, 5 ints each (cta, frame, strip column, y0, y1)
+int fused_debug_units(int sm_count, int n_frames, int H, int W, int row0, int row1, bool rows_mode, bool allow_linear, std::vector<int> &units, int &grid)
+{
+    FusedParams P{};
+    P.n_frames = n_frames; P.H = H; P.W = W; P.ys = row0; P.ye = row1;
+    if (sm_count < 1 || n_frames < 1 || W < 1 || row0 < 0 || row1 > H || row0 >= row1 || (rows_mode && n_frames != 1)) return -1;
+    if (plan_units(P, sm_count, allow_linear, rows_mode, grid) != cudaSuccess) return -1;
+    units.clear();
+    for (int u = 0; u < P.n_units; ++u) {
+        const UnitGeo g = rows_mode ? unit_geo<true>(P, u, H, grid) : unit_geo<false>(P, u, H, grid);
+        if (!g.ok) continue;
+        const int v[5] = {u % grid, g.f, g.strip, g.y0, g.y1};
+        units.insert(units.end(), v, v + 5);
+    }
+    return 0;
+}
+
 cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_out, int n, int H, int W, cudaStream_t st,
                           long long *launches, const FusedRows *rows)
 {
@@ -1191,60 +1270,8 @@ cudaError_t fused_forward(const FusedModel *fm, const uint8_t *d_in, uint8_t *d_
         P.flag_bot = rows->d_bot ? rows->flag_bot : nullptr;
         P.pub = rows->pub; P.done = rows->done; P.done_ctr = rows->done_ctr; P.seq = rows->seq;
     }
-    const int rows_out = P.ye - P.ys;
-    P.nstrips = (W + WT - 1) / WT;
     int grid = 1;
-    if (rows) {
-        // one line of nstrips * rows_out row-iterations, cut into equal chunks (rows_unit): every SM gets the same number
-        // of rows; a chunk pays the PIPE iterations of pipeline fill once per strip column it touches (never below 32 rows
-        // per CTA)
-        const long long total = (long long)P.nstrips * rows_out;
-        if (total > 0x3fffffffll) return cudaErrorInvalidValue;
-        grid = (int)std::max<long long>(1, std::min<long long>(fm->sm_count, total / 32));
-        P.seg_rows = (int)((total + grid - 1) / grid);                 // the chunk
-        grid = (int)((total + P.seg_rows - 1) / P.seg_rows);
-        const int pieces = (P.seg_rows + rows_out - 1) / rows_out + 1;  // strip columns a chunk can touch
-        P.nseg = 1;
-        P.n_units = grid * pieces;
-    } else {
-        // Row segments.  Units are dealt to the persistent CTAs round-robin, so the makespan is
-        // ceil(units / SMs) * (rows per segment + PIPE) row-iterations; pick the cut that minimises it
-        // (never below 16 rows per segment: every segment pays PIPE iterations of pipeline fill).
-        const long long cols = (long long)n * P.nstrips;
-        int nseg = 1;
-        {
-            long long best = -1;
-            const int max_seg = std::max(1, std::min(rows_out / 16, 256));
-            for (int c = 1; c <= max_seg; ++c) {
-                const int rws = (rows_out + c - 1) / c, real = (rows_out + rws - 1) / rws;
-                const long long waves = (cols * real + fm->sm_count - 1) / fm->sm_count;
-                const long long cost = waves * (rws + PIPE);
-                if (best < 0 || cost < best) { best = cost; nseg = c; }
-            }
-        }
-        P.seg_rows = (rows_out + nseg - 1) / nseg;
-        P.nseg = (rows_out + P.seg_rows - 1) / P.seg_rows;
-        const long long units = cols * P.nseg;
-        if (units > 0x7fffffffll) return cudaErrorInvalidValue;
-        P.n_units = (int)units;
-        grid = (int)std::min<long long>(units, fm->sm_count);
-        // ... or the line of cols * H row-iterations cut into one equal chunk per SM (see unit_geo): no idle SMs in the last
-        // wave, one pipeline fill per strip column a chunk touches.  64 x 1080p: 7585 iterations per SM against 7658.
-        const long long total = cols * rows_out, g2 = std::max<long long>(1, std::min<long long>(fm->sm_count, total / 32));
-        const long long chunk = (total + g2 - 1) / g2, pieces = (chunk + rows_out - 1) / rows_out + 1;
-        const long long cost_equal = (units + grid - 1) / grid * (P.seg_rows + PIPE);
-        if (fm->env_linear && total <= 0x3fffffffll && chunk + pieces * PIPE < cost_equal) {
-            P.linear = 1;
-            P.seg_rows = (int)chunk;
-            grid = (int)((total + chunk - 1) / chunk);
-            P.nseg = 1;
-            P.n_units = grid * (int)pieces;
-            const long long per = (cols + grid - 1) / grid;               // columns per chunk, rounded up
-            P.perm_q = (int)((cols + per - 1) / per);
-            P.perm_s0 = (int)(cols / P.perm_q);
-            P.perm_r = (int)(cols % P.perm_q);
-        }
-    }
+    if (const cudaError_t e = plan_units(P, fm->sm_count, fm->env_linear, rows != nullptr, grid)) return e;
     const bool prof = fm->env_profile;
     P.dbg = nullptr;
     P.dbg_flags = fm->env_experiment;

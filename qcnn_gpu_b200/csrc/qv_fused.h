@@ -37,5 +37,7 @@ int fused_take_failure(const FusedModel *fm);
 
 // Test hook (no GPU): weight image, per-phase MMA operand table (bases 0) and constants as the host builds them.
 void fused_debug_tables(const ModelHost &m, std::vector<uint8_t> &wimg, std::vector<uint32_t> &ops, std::vector<int32_t> &consts);
+// test hook: how a launch is dealt out to the persistent CTAs (5 ints per unit: cta, frame, strip column, y0, y1); no GPU needed
+int fused_debug_units(int sm_count, int n_frames, int H, int W, int row0, int row1, bool rows_mode, bool allow_linear, std::vector<int> &units, int &grid);
 
 }  // namespace qv
